@@ -1,0 +1,110 @@
+"""CPU: pin the oracle (oracle/) against golden vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py).  Tolerances are stated per test; fp32 reference vs fp32 restatement
+differs only by summation order / libm exp."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+
+def relerr(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+@pytest.mark.parametrize("tag", ["pow2", "ragged", "tiny", "f64"])
+def test_pscan_blelloch_matches_reference(golden, tag):
+    """numpy restatement of the Blelloch sweeps (pscan.py:37-224) == reference, bit-for-bit op order."""
+    g = golden(f"pscan_{tag}")
+    H, Hpad = O.pscan_forward(g["A"], g["X"])
+    tol = 1e-12 if tag == "f64" else 2e-6
+    assert relerr(H, g["H"]) <= tol
+    gA, gX = O.pscan_backward(g["A"], Hpad, g["gH"])
+    assert relerr(gA, g["gA"]) <= tol
+    assert relerr(gX, g["gX"]) <= tol
+
+
+@pytest.mark.parametrize("tag", ["pow2", "ragged", "tiny", "f64"])
+def test_pscan_sequential_matches_reference(golden, tag):
+    """sequential C recurrence == reference pscan fwd/bwd (1.3e-7 fp32 / 2e-16 fp64)."""
+    g = golden(f"pscan_{tag}")
+    tol = 1e-12 if tag == "f64" else 5e-6
+    H = O.pscan_seq_fwd(g["A"], g["X"])
+    assert relerr(H, g["H"]) <= tol
+    gA, gX = O.pscan_seq_bwd(g["A"], H, g["gH"])
+    assert relerr(gA, g["gA"]) <= tol
+    assert relerr(gX, g["gX"]) <= tol
+
+
+@pytest.mark.parametrize("tag", ["init", "randA", "short"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_selscan_fwd_matches_reference(golden, tag, dtype):
+    g = golden(f"selscan_{tag}")
+    y = O.selective_scan_fwd(g["x"], g["delta"], g["A"], g["Bm"], g["Cm"], g["D"], dtype=dtype)
+    assert relerr(y, g["y_pscan"]) <= 5e-6
+    assert relerr(y, g["y_seq"]) <= 5e-6
+    out = O.selective_scan_fwd(g["x"], g["delta"], g["A"], g["Bm"], g["Cm"], g["D"], z=g["z"], dtype=dtype)
+    assert relerr(out, g["out"]) <= 5e-6
+    y2 = O.selective_scan_pscan(g["x"], g["delta"], g["A"], g["Bm"], g["Cm"], g["D"])
+    assert relerr(y2, g["y_pscan"]) <= 5e-6
+
+
+@pytest.mark.parametrize("tag", ["init", "randA", "short"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_selscan_bwd_matches_reference_autograd(golden, tag, dtype):
+    g = golden(f"selscan_{tag}")
+    r = O.selective_scan_bwd(g["x"], g["delta"], g["A"], g["Bm"], g["Cm"], g["D"], g["dout"], z=g["z"], dtype=dtype)
+    for k in ("dx", "ddelta", "dz", "dA", "dB", "dC", "dD"):
+        assert relerr(r[k], g[k]) <= 2e-5, k
+
+
+def test_selscan_state_passing():
+    """splitting L with (h0 -> hT) state passing reproduces the unsplit scan (used by the L-split path)."""
+    rng = np.random.default_rng(0)
+    B, L, ED, N = 2, 50, 8, 16
+    x, z = rng.standard_normal((2, B, L, ED))
+    delta = np.log1p(np.exp(rng.standard_normal((B, L, ED)) - 3))
+    A = -np.exp(rng.standard_normal((ED, N)) * 0.5)
+    Bm, Cm = rng.standard_normal((2, B, L, N))
+    D = rng.standard_normal(ED)
+    full = O.selective_scan_fwd(x, delta, A, Bm, Cm, D, z=z, dtype=np.float64)
+    a, h = O.selective_scan_fwd(x[:, :20], delta[:, :20], A, Bm[:, :20], Cm[:, :20], D, z=z[:, :20], dtype=np.float64,
+                                return_state=True)
+    b = O.selective_scan_fwd(x[:, 20:], delta[:, 20:], A, Bm[:, 20:], Cm[:, 20:], D, z=z[:, 20:], h0=h,
+                             dtype=np.float64)
+    assert relerr(np.concatenate([a, b], 1), full) <= 1e-13
+
+
+def test_mamba_block_matches_reference(golden):
+    g = golden("mamba_block")
+    p = {k[len("sd.mixer."):]: v for k, v in g.items() if k.startswith("sd.mixer.")}
+    y = O.mamba_block_forward(g["x"], p)
+    assert relerr(y, g["y_mixer"]) <= 1e-5
+    yr = O.mamba_block_forward(O.rmsnorm(g["x"], g["sd.norm.weight"]), p) + g["x"]
+    assert relerr(yr, g["y_res"]) <= 1e-5
+
+
+@pytest.mark.parametrize("tag", ["8x8", "16x16", "20x20", "7x7", "8x12"])
+def test_ffm_matches_reference(golden, tag):
+    """extract_frequency2 incl. the negative-slice wrap (common.py:44-56) and the fp16 real cast (:66-67)."""
+    g = golden(f"ffm_{tag}")
+    low, high = O.extract_frequency2(g["img"])
+    assert low.dtype == np.float16 and high.dtype == np.float16
+    # fp16 outputs: allow 1 fp16 ulp of the largest magnitude (pocketfft vs numpy fft rounding)
+    assert relerr(low, g["low"]) <= 2e-3
+    assert relerr(high, g["high"]) <= 2e-3
+    fs = O.fourier_transform(g["img"])
+    assert relerr(fs.real, g["fs_re"]) <= 1e-5 and relerr(fs.imag, g["fs_im"]) <= 1e-5
+    # mask restatement == slice restatement
+    kh, kl = O.ffm_masks(*g["img"].shape[-2:])
+    fsh = np.fft.fftshift(np.fft.fftn(g["img"], axes=(-2, -1)), axes=(-2, -1))
+    hi2 = np.fft.ifftn(np.fft.ifftshift(fsh * kh, axes=(-2, -1)), axes=(-2, -1)).real
+    lo2 = np.fft.ifftn(np.fft.ifftshift(fsh * kl, axes=(-2, -1)), axes=(-2, -1)).real
+    assert relerr(hi2, g["high"].astype(np.float32)) <= 2e-3
+    assert relerr(lo2, g["low"].astype(np.float32)) <= 2e-3 or np.max(np.abs(g["low"])) < 1e-3
+
+
+def test_separation_loss_matches_reference(golden):
+    g = golden("seploss")
+    assert abs(O.separation_loss(g["M"]) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
