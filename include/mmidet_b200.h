@@ -1,0 +1,118 @@
+/*
+ * include/mmidet_b200.h -- C ABI of libmmidet_b200.so (B200 / sm_100a).
+ *
+ * Drop-in boundary for MMI-Det's cross-modal fusion hot path.  The reference is pure Python/PyTorch and has
+ * no FFI of its own; every entry point below names the reference symbol it replaces.  The
+ * Python host side (mmi-det_b200/*.py) binds these with ctypes and mirrors the reference's operator interface.
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers valid on the device that owns `stream` (a cudaStream_t passed as
+ *     void*; NULL = legacy default stream) unless the name ends in `_host`.
+ *   - The caller (PyTorch) owns every buffer; the library never allocates or frees device memory, except the
+ *     `_host` entry points which own a private, reusable staging workspace.
+ *   - Return value: 0 = success; non-zero = error (MMI_ERR_*), message via mmi_last_error() (thread-local).
+ *   - dtype: MMI_F32 / MMI_BF16 / MMI_F16 is the I/O element type of x, delta, z, B, C, out and their gradients;
+ *     A, D, states and all accumulation are fp32.
+ *   - Row pitches (`*_ld`) are in ELEMENTS; tensors (B, L, ED) are addressed as row (b*L + t), column d, so a
+ *     chunk()/slice view along the channel axis is passed without a copy.  Pitch*sizeof(elem) and the base
+ *     address must be multiples of 16 bytes (TMA bulk-copy requirement), ED a multiple of 8.
+ *   - No CPU fallback exists: on a machine without an sm_100 device every compute entry returns MMI_ERR_CUDA.
+ */
+#ifndef MMIDET_B200_H
+#define MMIDET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { MMI_F32 = 0, MMI_BF16 = 1, MMI_F16 = 2 };
+enum { MMI_OK = 0, MMI_ERR_ARG = 1, MMI_ERR_CUDA = 2, MMI_ERR_UNSUPPORTED = 3 };
+
+/* flags for the selective-scan entry points */
+enum {
+    MMI_FLAG_NO_GEOM = 1,      /* disable the geometric-A fast path (A[d,n] == (n+1)*A[d,0], the S4D-real init) */
+    MMI_FLAG_LPC_SHIFT = 4,    /* bits 4..7: force lanes-per-channel (1, 2 or 4); 0 = heuristic */
+    MMI_FLAG_LPC_MASK = 0xF0
+};
+
+const char *mmi_last_error(void);
+int mmi_version(void);
+/* number of SMs / compute capability of the current device; returns MMI_ERR_CUDA when no device is usable */
+int mmi_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused selective scan (+ optional SiLU gate).
+ * Replaces MambaBlock.selective_scan (models/mamba.py:212-233: exp(delta*A), delta*B*x, pscan, hs@C, +D*x) and,
+ * when z != NULL, the gate `y * silu(z)` of MambaBlock.forward (models/mamba.py:184-186).
+ *   x, delta, z, out : (B, L, ED) dtype, row pitches x_ld, delta_ld, z_ld, out_ld
+ *   A (ED, N) fp32 [= -exp(A_log), models/mamba.py:196], Bm, Cm (B, L, N) dtype contiguous, D (ED) fp32
+ *   h0   (nullable) : (B, ED, N) fp32 initial state (reference: zeros, models/mamba.py:252)
+ *   hT   (nullable) : (B, ED, N) fp32 final state h[L-1]
+ *   chk  (nullable) : (B, ceil(L/chunk), ED, N) fp32; chk[b,j] = state entering step j*chunk.  Written for the
+ *                     backward pass, which recomputes states chunk by chunk instead of materialising (B,L,ED,N).
+ *   chunk           : checkpoint interval, must equal mmi_selscan_chunk() when chk != NULL
+ *   N must be 16 (the reference default d_state, models/mamba.py:35).
+ * --------------------------------------------------------------------------------------------------------- */
+int mmi_selscan_chunk(void);
+int mmi_selscan_fwd(const void *x, const void *delta, const void *z, const float *A, const void *Bm, const void *Cm,
+                    const float *D, const float *h0, void *out, float *hT, float *chk, int B, int L, int ED, int N,
+                    int64_t x_ld, int64_t delta_ld, int64_t z_ld, int64_t out_ld, int chunk, int dtype, int flags,
+                    void *stream);
+
+/* Backward of the above.  Replaces autograd through models/mamba.py:222-231 and PScan.backward
+ * (models/pscan.py:189-224: reverse scan with A shifted left, gradA = H[t-1]*G[t], gradX = G).
+ *   dout, dx, ddelta, dz : (B, L, ED) dtype (pitches dout_ld, and ED-contiguous outputs), dz nullable iff z is
+ *   dBm, dCm : (B, L, N) dtype; dA (ED, N) fp32; dD (ED) fp32   -- all OVERWRITTEN (not accumulated)
+ *   chk      : checkpoints written by mmi_selscan_fwd with the same chunk
+ *   ws       : device workspace of at least mmi_selscan_bwd_ws_bytes(B, L, ED, N) bytes (partial reductions) */
+int64_t mmi_selscan_bwd_ws_bytes(int B, int L, int ED, int N);
+int mmi_selscan_bwd(const void *x, const void *delta, const void *z, const float *A, const void *Bm, const void *Cm,
+                    const float *D, const void *dout, const float *chk, void *dx, void *ddelta, void *dz, float *dA,
+                    void *dBm, void *dCm, float *dD, void *ws, int B, int L, int ED, int N, int64_t x_ld,
+                    int64_t delta_ld, int64_t z_ld, int64_t dout_ld, int chunk, int dtype, int flags, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Materialised linear recurrence  H[t] = A[t]*H[t-1] + X[t]  -- parity API for `pscan` (models/pscan.py:226).
+ *   A, X, H : (B, L, D, N) fp32 contiguous.  Inputs are not modified (reference clones, pscan.py:167-174).
+ * mmi_pscan_bwd replaces PScan.backward (models/pscan.py:189-224): gA[t] = H[t-1]*G[t] (gA[0]=0), gX = G with
+ *   G[t] = gH[t] + A[t+1]*G[t+1].
+ * --------------------------------------------------------------------------------------------------------- */
+int mmi_pscan_fwd(const float *A, const float *X, float *H, int B, int L, int D, int N, void *stream);
+int mmi_pscan_bwd(const float *A, const float *H, const float *gH, float *gA, float *gX, int B, int L, int D, int N,
+                  void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Fusion Focus Module Fourier step.  Replaces extract_frequency2 (models/common.py:37-69):
+ *   fftn -> fftshift -> rectangular masks (with the negative-slice wrap of :44-56) -> ifftshift -> ifftn ->
+ *   real part -> fp16, for the low- and the high-pass image in one pass, plus the product high*fea used at
+ *   models/common.py:440-441.  The box masks are separable, so the low-pass is evaluated directly as
+ *   low = Re(Pr . x . Pc) with the small real/complex projection matrices of the kept bins; high = x - low
+ *   whenever the two masks are complementary (always true for the reference's masks).
+ *   img (BC, H, W) dtype contiguous; low, high (BC, H, W) fp16; high_mul (nullable) (BC, H, W) fp32 = high*img.
+ *   H, W <= 64.
+ * --------------------------------------------------------------------------------------------------------- */
+int mmi_ffm_extract(const void *img, void *low, void *high, float *high_mul, int BC, int H, int W, int dtype,
+                    void *stream);
+
+/* Separation loss (models/common.py:128-139) in closed form:
+ *   sum_{i<j} M_i.M_j / (l(l-1)) = (|sum_i M_i|^2 - sum_i |M_i|^2) / (2 l (l-1)).   M (l, K) fp32 -> loss[0]. */
+int mmi_separation_loss(const float *M, float *loss, int l, int K, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Host-buffer entry (end-to-end path used by bench.py `e2e`): same maths as mmi_selscan_fwd followed by
+ * mmi_selscan_bwd, with every pointer a HOST pointer (pinned memory recommended).  Copies inputs H2D, runs
+ * forward + backward on an internal stream, copies out/dx/ddelta/dz/dB/dC/dA/dD back and synchronises.
+ * The staging workspace is owned by the library and reused across calls; mmi_host_workspace_free releases it.
+ * --------------------------------------------------------------------------------------------------------- */
+int mmi_selscan_fwd_bwd_host(const void *x, const void *delta, const void *z, const float *A, const void *Bm,
+                             const void *Cm, const float *D, const void *dout, void *out, void *dx, void *ddelta,
+                             void *dz, float *dA, void *dBm, void *dCm, float *dD, int B, int L, int ED, int N,
+                             int dtype, int flags);
+void mmi_host_workspace_free(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMIDET_B200_H */

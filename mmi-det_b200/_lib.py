@@ -1,0 +1,100 @@
+"""ctypes loader and in-tree builder for libmmidet_b200.so (the C ABI of include/mmidet_b200.h).
+
+There is deliberately no CPU / eager fallback: if the library is missing, or no sm_100 device is present,
+every operator raises RuntimeError."""
+from __future__ import annotations
+
+import ctypes
+import glob
+import os
+import subprocess
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_DIR)
+SO_PATH = os.path.join(_DIR, "libmmidet_b200.so")
+CSRC = os.path.join(_DIR, "csrc")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
+
+MMI_F32, MMI_BF16, MMI_F16 = 0, 1, 2
+FLAG_NO_GEOM = 1
+FLAG_LPC_SHIFT = 4
+
+_lib = None
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def needs_build() -> bool:
+    if not os.path.exists(SO_PATH):
+        return True
+    t = os.path.getmtime(SO_PATH)
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) + \
+        glob.glob(os.path.join(_ROOT, "include", "*.h"))
+    return any(os.path.getmtime(f) > t for f in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> mmi-det_b200/libmmidet_b200.so (in-tree)."""
+    if not force and not needs_build():
+        return SO_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH] + sources()
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    return SO_PATH
+
+
+_c = ctypes
+_vp, _i, _i64, _fp = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_void_p
+
+_SIGNATURES = {
+    "mmi_last_error": (_c.c_char_p, []),
+    "mmi_version": (_i, []),
+    "mmi_device_info": (_i, [_c.POINTER(_i)] * 3),
+    "mmi_selscan_chunk": (_i, []),
+    "mmi_selscan_fwd": (_i, [_vp] * 11 + [_i] * 4 + [_i64] * 4 + [_i] * 3 + [_vp]),
+    "mmi_selscan_bwd_ws_bytes": (_i64, [_i] * 4),
+    "mmi_selscan_bwd": (_i, [_vp] * 17 + [_i] * 4 + [_i64] * 4 + [_i] * 3 + [_vp]),
+    "mmi_pscan_fwd": (_i, [_vp] * 3 + [_i] * 4 + [_vp]),
+    "mmi_pscan_bwd": (_i, [_vp] * 5 + [_i] * 4 + [_vp]),
+    "mmi_ffm_extract": (_i, [_vp] * 4 + [_i] * 4 + [_vp]),
+    "mmi_separation_loss": (_i, [_vp] * 2 + [_i] * 2 + [_vp]),
+    "mmi_selscan_fwd_bwd_host": (_i, [_vp] * 16 + [_i] * 6),
+    "mmi_host_workspace_free": (None, []),
+}
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def load() -> ctypes.CDLL:
+    """Load the extension (building it first if sources are newer and nvcc is present). Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if needs_build():
+        try:
+            build()
+        except (FileNotFoundError, RuntimeError) as e:
+            if not os.path.exists(SO_PATH):
+                raise RuntimeError(f"libmmidet_b200.so is not built and cannot be built here: {e}") from e
+    lib = ctypes.CDLL(SO_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError => header/library mismatch, fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str = "libmmidet_b200") -> None:
+    if code != 0:
+        msg = load().mmi_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {code}): {msg}")

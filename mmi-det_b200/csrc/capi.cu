@@ -1,0 +1,152 @@
+// capi.cu -- the extern "C" boundary declared in include/mmidet_b200.h: argument validation, error strings,
+// dispatch to the kernel launchers.  No torch types, no allocation of caller-visible memory.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/mmidet_b200.h"
+#include "common.cuh"
+#include "selscan.h"
+
+namespace mmi {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return MMI_OK;
+    set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    return MMI_ERR_CUDA;
+}
+
+int sm_count() {
+    static int cached = 0;
+    if (cached) return cached;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        n <= 0) {
+        (void)cudaGetLastError();
+        return 148;  // B200
+    }
+    cached = n;
+    return n;
+}
+
+static int elem_size(int dtype) { return dtype == MMI_F32 ? 4 : (dtype == MMI_BF16 || dtype == MMI_F16) ? 2 : 0; }
+
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// every launch path funnels through here first: refuses to run on anything but sm_100 (no fallback of any kind)
+static int require_device() {
+    static int state = 0;  // 0 unknown, 1 ok
+    if (state == 1) return MMI_OK;
+    int dev = 0, major = 0;
+    if (int e = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return e;
+    if (int e = check_cuda(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev), "device attribute"))
+        return e;
+    if (major != 10) {
+        set_error("libmmidet_b200 is built for sm_100a only; current device has compute capability major %d", major);
+        return MMI_ERR_UNSUPPORTED;
+    }
+    state = 1;
+    return MMI_OK;
+}
+
+static int check_scan_args(const char *who, int B, int L, int ED, int N, int dtype, const void *const *ptrs,
+                           const int64_t *lds, int nptr) {
+    const int es = elem_size(dtype);
+    if (!es) { set_error("%s: unknown dtype %d", who, dtype); return MMI_ERR_ARG; }
+    if (B <= 0 || L <= 0 || ED <= 0) { set_error("%s: B, L, ED must be positive (B=%d L=%d ED=%d)", who, B, L, ED); return MMI_ERR_ARG; }
+    if (B > 65535) { set_error("%s: B=%d exceeds 65535", who, B); return MMI_ERR_ARG; }
+    if (N != kN) { set_error("%s: d_state N=%d unsupported (this build keeps N=%d states in registers)", who, N, kN); return MMI_ERR_UNSUPPORTED; }
+    if (ED % 8) { set_error("%s: ED=%d must be a multiple of 8", who, ED); return MMI_ERR_ARG; }
+    for (int i = 0; i < nptr; ++i) {
+        if (!ptrs[i]) continue;
+        if (!aligned16(ptrs[i])) { set_error("%s: tensor %d is not 16-byte aligned", who, i); return MMI_ERR_ARG; }
+        if (lds && lds[i] && ((lds[i] * es) % 16 || lds[i] < ED)) {
+            set_error("%s: row pitch %lld of tensor %d must be >= ED and a multiple of 16 bytes", who, (long long)lds[i], i);
+            return MMI_ERR_ARG;
+        }
+    }
+    return MMI_OK;
+}
+
+}  // namespace mmi
+
+using namespace mmi;
+
+extern "C" {
+
+const char *mmi_last_error(void) { return g_err; }
+int mmi_version(void) { return 100; }
+
+int mmi_device_info(int *sms, int *maj, int *min) {
+    int dev = 0;
+    if (int e = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return e;
+    int a = 0, b = 0, c = 0;
+    if (int e = check_cuda(cudaDeviceGetAttribute(&a, cudaDevAttrMultiProcessorCount, dev), "device attribute")) return e;
+    cudaDeviceGetAttribute(&b, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&c, cudaDevAttrComputeCapabilityMinor, dev);
+    if (sms) *sms = a;
+    if (maj) *maj = b;
+    if (min) *min = c;
+    return MMI_OK;
+}
+
+int mmi_selscan_chunk(void) { return kChunk; }
+
+int mmi_selscan_fwd(const void *x, const void *delta, const void *z, const float *A, const void *Bm, const void *Cm,
+                    const float *D, const float *h0, void *out, float *hT, float *chk, int B, int L, int ED, int N,
+                    int64_t x_ld, int64_t delta_ld, int64_t z_ld, int64_t out_ld, int chunk, int dtype, int flags,
+                    void *stream) {
+    if (!x || !delta || !A || !Bm || !Cm || !D || !out) { set_error("mmi_selscan_fwd: null required pointer"); return MMI_ERR_ARG; }
+    const void *ptrs[] = {x, delta, z, out, Bm, Cm};
+    const int64_t lds[] = {x_ld, delta_ld, z ? z_ld : 0, out_ld, 0, 0};
+    if (int e = check_scan_args("mmi_selscan_fwd", B, L, ED, N, dtype, ptrs, lds, 6)) return e;
+    if (chk && chunk != kChunk) { set_error("mmi_selscan_fwd: chunk=%d, expected mmi_selscan_chunk()=%d", chunk, kChunk); return MMI_ERR_ARG; }
+    if (int e = require_device()) return e;
+    FwdParams p{};
+    p.x = x; p.delta = delta; p.z = z; p.Bm = Bm; p.Cm = Cm; p.A = A; p.D = D; p.h0 = h0;
+    p.out = out; p.hT = hT; p.chk = chk;
+    p.B = B; p.L = L; p.ED = ED;
+    p.x_ld = x_ld; p.d_ld = delta_ld; p.z_ld = z_ld; p.o_ld = out_ld;
+    p.flags = flags;
+    return selscan_fwd_launch(p, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int64_t mmi_selscan_bwd_ws_bytes(int B, int L, int ED, int N) {
+    (void)N;
+    if (B <= 0 || L <= 0 || ED <= 0) return 0;
+    return selscan_bwd_ws_bytes(B, L, ED);
+}
+
+int mmi_selscan_bwd(const void *x, const void *delta, const void *z, const float *A, const void *Bm, const void *Cm,
+                    const float *D, const void *dout, const float *chk, void *dx, void *ddelta, void *dz, float *dA,
+                    void *dBm, void *dCm, float *dD, void *ws, int B, int L, int ED, int N, int64_t x_ld,
+                    int64_t delta_ld, int64_t z_ld, int64_t dout_ld, int chunk, int dtype, int flags, void *stream) {
+    if (!x || !delta || !A || !Bm || !Cm || !D || !dout || !chk || !dx || !ddelta || !dA || !dBm || !dCm || !dD || !ws) {
+        set_error("mmi_selscan_bwd: null required pointer");
+        return MMI_ERR_ARG;
+    }
+    if ((z == nullptr) != (dz == nullptr)) { set_error("mmi_selscan_bwd: z and dz must both be given or both be NULL"); return MMI_ERR_ARG; }
+    const void *ptrs[] = {x, delta, z, dout, Bm, Cm, dx, ddelta, dz, dBm, dCm, chk, ws};
+    const int64_t lds[] = {x_ld, delta_ld, z ? z_ld : 0, dout_ld, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (int e = check_scan_args("mmi_selscan_bwd", B, L, ED, N, dtype, ptrs, lds, 13)) return e;
+    if (chunk != kChunk) { set_error("mmi_selscan_bwd: chunk=%d, expected mmi_selscan_chunk()=%d", chunk, kChunk); return MMI_ERR_ARG; }
+    if (int e = require_device()) return e;
+    BwdParams p{};
+    p.x = x; p.delta = delta; p.z = z; p.Bm = Bm; p.Cm = Cm; p.dout = dout; p.A = A; p.D = D; p.chk = chk;
+    p.dx = dx; p.ddelta = ddelta; p.dz = dz; p.dBm = dBm; p.dCm = dCm; p.dA = dA; p.dD = dD;
+    p.B = B; p.L = L; p.ED = ED;
+    p.x_ld = x_ld; p.d_ld = delta_ld; p.z_ld = z_ld; p.g_ld = dout_ld;
+    p.flags = flags;
+    return selscan_bwd_launch(p, dtype, ws, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

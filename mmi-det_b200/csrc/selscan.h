@@ -1,0 +1,39 @@
+// selscan.h -- parameter blocks and launch entry points of the fused selective-scan kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mmi {
+
+constexpr int kChunk = 16;    // state-checkpoint interval in timesteps (== backward tile length)
+constexpr int kFwdTile = 32;  // forward tile length, a multiple of kChunk
+
+struct FwdParams {
+    const void *x, *delta, *z, *Bm, *Cm;
+    const float *A, *D, *h0;
+    void *out;
+    float *hT, *chk;
+    int B, L, ED;
+    int64_t x_ld, d_ld, z_ld, o_ld;
+    int flags;
+};
+
+struct BwdParams {
+    const void *x, *delta, *z, *Bm, *Cm, *dout;
+    const float *A, *D, *chk;
+    void *dx, *ddelta, *dz, *dBm, *dCm;
+    float *dA, *dD;
+    float *ws_bc;  // (B, L, ntile_c, 2, N) fp32 per-CTA partial dB/dC
+    float *ws_ad;  // (B, ED, N + 1) fp32 per-batch partial dA / dD
+    int B, L, ED;
+    int ntile_c;   // channel tiles per row (grid.x)
+    int64_t x_ld, d_ld, z_ld, g_ld;
+    int flags;
+};
+
+int selscan_fwd_launch(const FwdParams &p, int dtype, cudaStream_t st);
+int selscan_bwd_launch(BwdParams p, int dtype, void *ws, cudaStream_t st);
+int64_t selscan_bwd_ws_bytes(int B, int L, int ED);
+int sm_count();
+
+}  // namespace mmi

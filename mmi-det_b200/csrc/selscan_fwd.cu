@@ -1,0 +1,285 @@
+// selscan_fwd.cu -- fused selective scan forward for sm_100a.
+//
+// Replaces MambaBlock.selective_scan (+ the SiLU gate) of the reference, models/mamba.py:212-233 and :184-186:
+//     a[t,n] = exp(delta[t,d] * A[d,n]);  u[t,n] = delta[t,d] * B[t,n] * x[t,d]
+//     h[t,n] = a[t,n] * h[t-1,n] + u[t,n]
+//     y[t,d] = sum_n C[t,n] h[t,n] + D[d] x[t,d];   out = y * silu(z)
+// The reference materialises four (B,L,ED,N) tensors and runs ~76 strided kernels of a Blelloch scan
+// (models/pscan.py:37-92); here nothing of size N is ever written except one state checkpoint per kChunk steps.
+//
+// Mapping (channels-last): a group of LPC adjacent lanes owns one channel d and N/LPC of its states in
+// registers for the whole sequence; a warp owns 32/LPC adjacent channels; a CTA owns NW warps = CH channels of one
+// batch element and walks t = 0..L-1.  Tiles [TC timesteps x CH channels] of x / delta / z and [TC x N] of B / C
+// are staged into shared memory by the TMA engine (cp.async.bulk.tensor 2-D tiles, one mbarrier per stage, a
+// STAGES-deep ring), so
+// HBM latency is covered by bytes in flight, not by thread count.  The recurrence, the C.h readout, the D skip and
+// the gate run on packed fp32x2 (FFMA2).  exp() is MUFU ex2 on delta*A*log2(e); when a channel's A row is geometric,
+// A[d,n] = (n+1) A[d,0] (the S4D-real init of models/mamba.py:158-159, which the reference training loop never
+// updates), a[t,n] = r^(n+1) needs one ex2 per step instead of N (detected on the device, per CTA).
+#include <cstring>
+
+#include "common.cuh"
+#include "selscan.h"
+#include "../../include/mmidet_b200.h"
+
+namespace mmi {
+
+struct FwdMaps {
+    CUtensorMap x, d, z, B, C;
+};
+
+template <typename T, int LPC, int NW, int TC, int STAGES> struct FwdLayout {
+    static constexpr int N = kN, NS = N / LPC, CPW = 32 / LPC, CH = NW * CPW;
+    static constexpr int STAGE_ELEMS = TC * (3 * CH + 2 * N);
+    static constexpr size_t STAGE_BYTES = size_t(STAGE_ELEMS) * sizeof(T);
+    static constexpr size_t BC32_BYTES = sizeof(T) == 2 ? size_t(2) * TC * N * 4 : 0;
+    static constexpr size_t BAR_OFF = STAGES * STAGE_BYTES + BC32_BYTES;
+    static constexpr size_t SMEM = BAR_OFF + STAGES * sizeof(uint64_t);
+};
+
+template <typename T, int LPC, int NW, int TC, int STAGES, bool GEOM>
+__device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, unsigned char *smem,
+                                         const float (&A2)[kN / LPC],
+                                         float A2base, float Dd, int c0, int chw, int b, int cl, int c, bool active,
+                                         int sub, int warp, int lane) {
+    using Lay = FwdLayout<T, LPC, NW, TC, STAGES>;
+    constexpr int N = kN, NS = Lay::NS, CH = Lay::CH, NP = NS / 2;
+    T *stage0 = reinterpret_cast<T *>(smem);
+    float *bc32 = reinterpret_cast<float *>(smem + STAGES * Lay::STAGE_BYTES);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + Lay::BAR_OFF);
+
+    const int L = p.L, ED = p.ED;
+    const bool has_z = p.z != nullptr;
+    const int ntiles = (L + TC - 1) / TC, nchk = (L + kChunk - 1) / kChunk;
+    T *gout = static_cast<T *>(p.out);
+    const int64_t row_b = int64_t(b) * L;
+
+    auto issue = [&](int s, int ti) {  // one elected lane: 5 TMA tile loads arriving on full[s]
+        T *sx = stage0 + size_t(s) * Lay::STAGE_ELEMS, *sd = sx + TC * CH, *sz = sd + TC * CH, *sB = sz + TC * CH,
+          *sC = sB + TC * N;
+        const int row0 = int(row_b) + ti * TC;
+        const uint32_t total = uint32_t(TC) * CH * sizeof(T) * (has_z ? 3u : 2u) + 2u * TC * N * sizeof(T);
+        mbar_arrive_expect_tx(&full[s], total);
+        tma_load_2d(sx, &tm.x, c0, row0, &full[s]);
+        tma_load_2d(sd, &tm.d, c0, row0, &full[s]);
+        if (has_z) tma_load_2d(sz, &tm.z, c0, row0, &full[s]);
+        tma_load_2d(sB, &tm.B, 0, row0, &full[s]);
+        tma_load_2d(sC, &tm.C, 0, row0, &full[s]);
+    };
+
+    // state
+    float2 h2[NP];
+    {
+        const float *h0 = p.h0 ? p.h0 + (int64_t(b) * ED + (active ? c : 0)) * N + sub * NS : nullptr;
+#pragma unroll
+        for (int k = 0; k < NP; ++k) h2[k] = h0 ? make_float2(h0[2 * k], h0[2 * k + 1]) : make_float2(0.f, 0.f);
+    }
+    float2 A2p[NP];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) A2p[k] = make_float2(A2[2 * k], A2[2 * k + 1]);
+
+    if (threadIdx.x == 0)
+        for (int s = 0; s < STAGES && s < ntiles; ++s) issue(s, s);
+
+    for (int it = 0; it < ntiles; ++it) {
+        const int s = it % STAGES;
+        const int t0 = it * TC, tl = min(TC, L - t0);
+        const T *sx = stage0 + size_t(s) * Lay::STAGE_ELEMS, *sd = sx + TC * CH, *sz = sd + TC * CH, *sB = sz + TC * CH,
+                *sC = sB + TC * N;
+        mbar_wait(&full[s], (it / STAGES) & 1);
+
+        const float *fB, *fC;
+        if constexpr (sizeof(T) == 2) {  // widen B / C once per CTA instead of once per lane
+            for (int i = threadIdx.x; i < 2 * TC * N; i += NW * 32) bc32[i] = to_f32<T>(sB[i]);  // sB, sC contiguous
+            __syncthreads();
+            fB = bc32;
+            fC = bc32 + TC * N;
+        } else {
+            fB = reinterpret_cast<const float *>(sB);
+            fC = reinterpret_cast<const float *>(sC);
+        }
+
+        auto checkpoint = [&](int t) {  // state entering step t0 + t, one per kChunk steps
+            if (p.chk && active) {
+                float4 *ck = reinterpret_cast<float4 *>(p.chk + ((int64_t(b) * nchk + (t0 + t) / kChunk) * ED + c) * N + sub * NS);
+#pragma unroll
+                for (int k = 0; k < NP / 2; ++k)
+                    __stcs(ck + k, make_float4(h2[2 * k].x, h2[2 * k].y, h2[2 * k + 1].x, h2[2 * k + 1].y));
+            }
+        };
+
+        auto step = [&](int t) {
+            const float xv = to_f32<T>(sx[t * CH + cl]);
+            const float dv = to_f32<T>(sd[t * CH + cl]);
+            float2 Bv[NP], Cv[NP];
+            {
+                const float4 *bp = reinterpret_cast<const float4 *>(fB + t * N + sub * NS);
+                const float4 *cp = reinterpret_cast<const float4 *>(fC + t * N + sub * NS);
+#pragma unroll
+                for (int k = 0; k < NP / 2; ++k) {
+                    const float4 bb = bp[k], cc = cp[k];
+                    Bv[2 * k] = make_float2(bb.x, bb.y);
+                    Bv[2 * k + 1] = make_float2(bb.z, bb.w);
+                    Cv[2 * k] = make_float2(cc.x, cc.y);
+                    Cv[2 * k + 1] = make_float2(cc.z, cc.w);
+                }
+            }
+            float2 a2[NP];
+            if constexpr (GEOM) {
+                const float r = ex2(dv * A2base);
+                const float q = (LPC == 1) ? r : ex2(dv * A2[0]);  // r^(sub*NS + 1)
+                const float2 rr = splat2(r * r);
+                a2[0] = make_float2(q, q * r);
+#pragma unroll
+                for (int k = 1; k < NP; ++k) a2[k] = mul2(a2[k - 1], rr);
+            } else {
+                const float2 dv2 = splat2(dv);
+#pragma unroll
+                for (int k = 0; k < NP; ++k) {
+                    const float2 e = mul2(dv2, A2p[k]);
+                    a2[k] = make_float2(ex2(e.x), ex2(e.y));
+                }
+            }
+            const float2 dx2 = splat2(dv * xv);
+            float2 ya = make_float2(0.f, 0.f), yb = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+                h2[k] = fma2(a2[k], h2[k], mul2(dx2, Bv[k]));
+                if (k & 1) yb = fma2(Cv[k], h2[k], yb);
+                else ya = fma2(Cv[k], h2[k], ya);
+            }
+            ya = add2(ya, yb);
+            float y = ya.x + ya.y;
+            if constexpr (LPC >= 2) y += __shfl_xor_sync(0xffffffffu, y, 1);
+            if constexpr (LPC >= 4) y += __shfl_xor_sync(0xffffffffu, y, 2);
+            y = fmaf(Dd, xv, y);
+            if (has_z) {
+                const float zv = to_f32<T>(sz[t * CH + cl]);
+                y *= zv * sigmoidf_fast(zv);
+            }
+            if (active && sub == 0) st_cs(gout + (row_b + t0 + t) * p.o_ld + c, from_f32<T>(y));
+        };
+
+        if (tl == TC) {
+#pragma unroll
+            for (int tc = 0; tc < TC; tc += kChunk) {
+                checkpoint(tc);
+#pragma unroll 4
+                for (int t = tc; t < tc + kChunk; ++t) step(t);
+            }
+        } else {
+            for (int t = 0; t < tl; ++t) {
+                if (t % kChunk == 0) checkpoint(t);
+                step(t);
+            }
+        }
+
+        __syncthreads();  // every warp is done with stage s (and bc32)
+        if (threadIdx.x == 0 && it + STAGES < ntiles) issue(s, it + STAGES);
+    }
+
+    if (p.hT && active) {
+        float *hT = p.hT + (int64_t(b) * ED + c) * N + sub * NS;
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            hT[2 * k] = h2[k].x;
+            hT[2 * k + 1] = h2[k].y;
+        }
+    }
+}
+
+template <typename T, int LPC, int NW, int TC, int STAGES>
+__global__ void __launch_bounds__(NW * 32)
+    selscan_fwd_kernel(const FwdParams p, const __grid_constant__ FwdMaps tm) {
+    using Lay = FwdLayout<T, LPC, NW, TC, STAGES>;
+    constexpr int N = kN, NS = Lay::NS, CPW = Lay::CPW, CH = Lay::CH;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + Lay::BAR_OFF);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y, c0 = blockIdx.x * CH;
+    const int chw = min(CH, p.ED - c0);
+    const int sub = lane % LPC;
+    const int cl = warp * CPW + lane / LPC;
+    const int c = c0 + cl;
+    const bool active = c < p.ED;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+
+    // A row of this lane's states, pre-scaled by log2(e); geometric-row test (block-uniform decision)
+    const int cc = active ? c : p.ED - 1;
+    float A2[NS];
+    const float A2base = p.A[int64_t(cc) * N] * kLog2e;
+    bool ok = !(p.flags & MMI_FLAG_NO_GEOM);
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        A2[k] = p.A[int64_t(cc) * N + sub * NS + k] * kLog2e;
+        const float want = float(sub * NS + k + 1) * A2base;
+        ok = ok && (fabsf(A2[k] - want) <= 2e-6f * fabsf(want));
+    }
+    const float Dd = p.D[cc];
+    const bool geom = __syncthreads_and(ok);  // also publishes the mbarrier inits
+
+    if (geom)
+        fwd_body<T, LPC, NW, TC, STAGES, true>(p, tm, smem, A2, A2base, Dd, c0, chw, b, cl, c, active, sub, warp, lane);
+    else
+        fwd_body<T, LPC, NW, TC, STAGES, false>(p, tm, smem, A2, A2base, Dd, c0, chw, b, cl, c, active, sub, warp, lane);
+}
+
+template <typename T, int LPC> static int launch_fwd_t(const FwdParams &p, int dtype, cudaStream_t st) {
+    constexpr int NW = 2, TC = kFwdTile, STAGES = 4;
+    using Lay = FwdLayout<T, LPC, NW, TC, STAGES>;
+    auto kern = selscan_fwd_kernel<T, LPC, NW, TC, STAGES>;
+    if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Lay::SMEM)),
+                           "selscan_fwd smem attribute"))
+        return e;
+    const uint64_t rows = uint64_t(p.B) * p.L;
+    FwdMaps tm;
+    memset(&tm, 0, sizeof(tm));
+    if (int e = make_tmap_2d(&tm.x, p.x, dtype, rows, p.ED, p.x_ld * sizeof(T), TC, Lay::CH)) return e;
+    if (int e = make_tmap_2d(&tm.d, p.delta, dtype, rows, p.ED, p.d_ld * sizeof(T), TC, Lay::CH)) return e;
+    if (p.z)
+        if (int e = make_tmap_2d(&tm.z, p.z, dtype, rows, p.ED, p.z_ld * sizeof(T), TC, Lay::CH)) return e;
+    if (int e = make_tmap_2d(&tm.B, p.Bm, dtype, rows, kN, kN * sizeof(T), TC, kN)) return e;
+    if (int e = make_tmap_2d(&tm.C, p.Cm, dtype, rows, kN, kN * sizeof(T), TC, kN)) return e;
+    dim3 grid((p.ED + Lay::CH - 1) / Lay::CH, p.B);
+    kern<<<grid, NW * 32, Lay::SMEM, st>>>(p, tm);
+    return check_cuda(cudaGetLastError(), "selscan_fwd launch");
+}
+
+template <typename T> static int launch_fwd_lpc(const FwdParams &p, int dtype, int lpc, cudaStream_t st) {
+    switch (lpc) {
+        case 1: return launch_fwd_t<T, 1>(p, dtype, st);
+        case 2: return launch_fwd_t<T, 2>(p, dtype, st);
+        case 4: return launch_fwd_t<T, 4>(p, dtype, st);
+    }
+    set_error("selscan_fwd: lanes-per-channel must be 1, 2 or 4 (got %d)", lpc);
+    return MMI_ERR_ARG;
+}
+
+// Lanes per channel: fewest lanes (least replicated work) that still gives every SM sub-partition a warp.
+int pick_lpc(int B, int ED, int flags) {
+    const int forced = (flags & MMI_FLAG_LPC_MASK) >> MMI_FLAG_LPC_SHIFT;
+    if (forced) return forced;
+    const long warps1 = long(B) * ED / 32;
+    const long want = 3L * sm_count();
+    if (warps1 >= want) return 1;
+    if (2 * warps1 >= want) return 2;
+    return 4;
+}
+
+int selscan_fwd_launch(const FwdParams &p, int dtype, cudaStream_t st) {
+    const int lpc = pick_lpc(p.B, p.ED, p.flags);
+    switch (dtype) {
+        case MMI_F32: return launch_fwd_lpc<float>(p, dtype, lpc, st);
+        case MMI_BF16: return launch_fwd_lpc<__nv_bfloat16>(p, dtype, lpc, st);
+        case MMI_F16: return launch_fwd_lpc<__half>(p, dtype, lpc, st);
+    }
+    set_error("selscan_fwd: unknown dtype %d", dtype);
+    return MMI_ERR_ARG;
+}
+
+}  // namespace mmi

@@ -1,0 +1,121 @@
+"""Operator layer: torch.autograd.Function wrappers over the C ABI (include/mmidet_b200.h).
+
+selective_scan(x, delta, A, B, C, D, z=None) mirrors MambaBlock.selective_scan of the reference
+(models/mamba.py:212-233) -- same argument order, shapes and meaning -- with the SiLU gate of
+MambaBlock.forward (models/mamba.py:184-186) optionally fused through `z`.
+PyTorch is used for device memory, streams and autograd plumbing only; there is no eager fallback."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: _lib.MMI_F32, torch.bfloat16: _lib.MMI_BF16, torch.float16: _lib.MMI_F16}
+
+# launch counter: number of kernels of OURS enqueued through this module (bench.py reports it as gpu_launches)
+launches = 0
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _require_cuda(t, who):
+    if not t.is_cuda:
+        raise RuntimeError(f"{who}: expected a CUDA tensor; mmidet_b200 has no CPU path (got device {t.device})")
+
+
+def _rows(t: torch.Tensor, esz_mult: int = 16) -> torch.Tensor:
+    """Return `t` (B, L, E) in a layout the kernels can address as rows of pitch `ld` without copying when
+    possible: unit channel stride, batch stride == L * row stride, 16-byte aligned rows."""
+    B, L, E = t.shape
+    ok = t.stride(2) == 1 and (B == 1 or t.stride(0) == L * t.stride(1)) and t.stride(1) >= E \
+        and (t.stride(1) * t.element_size()) % 16 == 0 and t.data_ptr() % 16 == 0
+    return t if ok else t.contiguous()
+
+
+def selscan_chunk() -> int:
+    return _lib.load().mmi_selscan_chunk()
+
+
+def selscan_fwd_raw(x, delta, A, Bm, Cm, D, z=None, h0=None, want_state=False, want_chk=False, flags=0):
+    """Direct call of mmi_selscan_fwd. Returns (out, hT or None, chk or None)."""
+    global launches
+    lib = _lib.load()
+    _require_cuda(x, "selective_scan")
+    Bsz, L, ED = x.shape
+    N = A.shape[1]
+    dt = x.dtype
+    x, delta = _rows(x), _rows(delta.to(dt))
+    z = None if z is None else _rows(z.to(dt))
+    Bm, Cm = Bm.to(dt).contiguous(), Cm.to(dt).contiguous()
+    A, D = A.float().contiguous(), D.float().contiguous()
+    out = torch.empty((Bsz, L, ED), dtype=dt, device=x.device)
+    hT = torch.empty((Bsz, ED, N), dtype=torch.float32, device=x.device) if want_state else None
+    chunk = lib.mmi_selscan_chunk()
+    chk = torch.empty((Bsz, (L + chunk - 1) // chunk, ED, N), dtype=torch.float32, device=x.device) if want_chk else None
+    h0 = None if h0 is None else h0.float().contiguous()
+    _lib.check(lib.mmi_selscan_fwd(_ptr(x), _ptr(delta), _ptr(z), _ptr(A), _ptr(Bm), _ptr(Cm), _ptr(D), _ptr(h0),
+                                   _ptr(out), _ptr(hT), _ptr(chk), Bsz, L, ED, N, x.stride(1), delta.stride(1),
+                                   z.stride(1) if z is not None else 0, out.stride(1), chunk, _DT[dt], flags,
+                                   _stream(x)), "mmi_selscan_fwd")
+    launches += 1
+    return out, hT, chk, (x, delta, z, A, Bm, Cm, D)
+
+
+def selscan_bwd_raw(saved, chk, dout, flags=0):
+    """Direct call of mmi_selscan_bwd. `saved` is the normalised input tuple returned by selscan_fwd_raw."""
+    global launches
+    lib = _lib.load()
+    x, delta, z, A, Bm, Cm, D = saved
+    Bsz, L, ED = x.shape
+    N = A.shape[1]
+    dt = x.dtype
+    dout = _rows(dout.to(dt))
+    dx, dd = torch.empty((Bsz, L, ED), dtype=dt, device=x.device), torch.empty((Bsz, L, ED), dtype=dt, device=x.device)
+    dz = torch.empty((Bsz, L, ED), dtype=dt, device=x.device) if z is not None else None
+    dA, dD = torch.empty_like(A), torch.empty_like(D)
+    dB, dC = torch.empty_like(Bm), torch.empty_like(Cm)
+    ws = torch.empty(lib.mmi_selscan_bwd_ws_bytes(Bsz, L, ED, N), dtype=torch.uint8, device=x.device)
+    _lib.check(lib.mmi_selscan_bwd(_ptr(x), _ptr(delta), _ptr(z), _ptr(A), _ptr(Bm), _ptr(Cm), _ptr(D), _ptr(dout),
+                                   _ptr(chk), _ptr(dx), _ptr(dd), _ptr(dz), _ptr(dA), _ptr(dB), _ptr(dC), _ptr(dD),
+                                   _ptr(ws), Bsz, L, ED, N, x.stride(1), delta.stride(1),
+                                   z.stride(1) if z is not None else 0, dout.stride(1), lib.mmi_selscan_chunk(),
+                                   _DT[dt], flags, _stream(x)), "mmi_selscan_bwd")
+    launches += 2  # scan kernel + partial-reduction kernel
+    return dx, dd, dz, dA, dB, dC, dD
+
+
+class _SelectiveScan(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, delta, A, Bm, Cm, D, z, flags):
+        need = any(t is not None and t.requires_grad for t in (x, delta, A, Bm, Cm, D, z))
+        out, _, chk, saved = selscan_fwd_raw(x, delta, A, Bm, Cm, D, z=z, want_chk=need, flags=flags)
+        ctx.flags = flags
+        ctx.has_z = z is not None
+        ctx.in_dtypes = tuple(None if t is None else t.dtype for t in (x, delta, A, Bm, Cm, D, z))
+        if need:
+            sx, sd, sz, sA, sB, sC, sD = saved
+            ctx.save_for_backward(sx, sd, sA, sB, sC, sD, chk, *( [sz] if sz is not None else []))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        sx, sd, sA, sB, sC, sD, chk, *rest = ctx.saved_tensors
+        sz = rest[0] if rest else None
+        dx, dd, dz, dA, dB, dC, dD = selscan_bwd_raw((sx, sd, sz, sA, sB, sC, sD), chk, dout, flags=ctx.flags)
+        dts = ctx.in_dtypes
+        cast = lambda g, i: None if g is None else g.to(dts[i])
+        return cast(dx, 0), cast(dd, 1), cast(dA, 2), cast(dB, 3), cast(dC, 4), cast(dD, 5), (cast(dz, 6) if ctx.has_z else None), None
+
+
+def selective_scan(x, delta, A, B, C, D, z=None, flags: int = 0):
+    """Fused selective scan. Shapes as models/mamba.py:212-220: x, delta (B, L, ED); A (ED, N); B, C (B, L, N);
+    D (ED).  Returns y (B, L, ED) = hs @ C + D * x, times silu(z) when `z` (B, L, ED) is given."""
+    return _SelectiveScan.apply(x, delta, A, B, C, D, z, flags)

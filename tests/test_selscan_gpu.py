@@ -1,0 +1,188 @@
+"""GPU parity: the CUDA selective scan (through the C ABI) vs the CPU oracle and the reference goldens.
+
+Tolerances (north_star): rel-err <= 1e-4 for fp32 I/O, <= 2e-2 for bf16 I/O, measured as max|a-b|/max|b|
+against the fp64 oracle evaluated on the same (dtype-rounded) inputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from tests.util import relerr, scan_inputs
+
+pytestmark = pytest.mark.gpu
+
+TOL32 = 1e-4
+TOL16 = 2e-2
+
+
+def _t(a, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda().to(dtype)
+
+
+def _run(inp, dtype=torch.float32, gate=True, flags=0, grad=True):
+    from mmidet_b200 import ops
+    leaves = {k: _t(inp[k], torch.float32 if k in ("A", "D") else dtype) for k in ("x", "delta", "z", "A", "Bm", "Cm", "D")}
+    if grad:
+        for v in leaves.values():
+            v.requires_grad_(True)
+    out = ops.selective_scan(leaves["x"], leaves["delta"], leaves["A"], leaves["Bm"], leaves["Cm"], leaves["D"],
+                             z=leaves["z"] if gate else None, flags=flags)
+    res = {"out": out.detach().float().cpu().numpy()}
+    if grad:
+        out.backward(_t(inp["dout"], dtype))
+        names = dict(x="dx", delta="ddelta", z="dz", A="dA", Bm="dB", Cm="dC", D="dD")
+        for k, n in names.items():
+            if leaves[k].grad is not None:
+                res[n] = leaves[k].grad.detach().float().cpu().numpy()
+    torch.cuda.synchronize()
+    return res
+
+
+def _oracle(inp, gate=True, grad=True):
+    z = inp["z"] if gate else None
+    ref = {"out": O.selective_scan_fwd(inp["x"], inp["delta"], inp["A"], inp["Bm"], inp["Cm"], inp["D"], z=z,
+                                       dtype=np.float64)}
+    if grad:
+        ref.update(O.selective_scan_bwd(inp["x"], inp["delta"], inp["A"], inp["Bm"], inp["Cm"], inp["D"], inp["dout"],
+                                        z=z, dtype=np.float64))
+    return ref
+
+
+def _compare(res, ref, tol, keys=None):
+    bad = {}
+    for k in keys or res.keys():
+        if ref.get(k) is None:
+            continue
+        e = relerr(res[k], ref[k])
+        if not (e <= tol):
+            bad[k] = e
+    assert not bad, f"rel-err above {tol}: {bad}"
+
+
+@pytest.mark.parametrize("lpc", [1, 2, 4])
+@pytest.mark.parametrize("random_A", [False, True])
+@pytest.mark.parametrize("shape", [(2, 96, 64), (1, 16, 8), (3, 37, 24), (2, 257, 40), (1, 1, 16), (2, 15, 72)])
+def test_fwd_bwd_fp32_vs_oracle(shape, random_A, lpc):
+    """all lane mappings x geometric / general A path x ragged L (not a multiple of the 16-step chunk) and
+    ED not a multiple of the channel tile."""
+    B, L, ED = shape
+    inp = scan_inputs(B, L, ED, seed=L + ED, random_A=random_A)
+    res = _run(inp, flags=lpc << 4)
+    _compare(res, _oracle(inp), TOL32)
+
+
+@pytest.mark.parametrize("lpc", [1, 2, 4])
+def test_forced_general_path_on_geometric_A(lpc):
+    """MMI_FLAG_NO_GEOM: the N-exponential path must agree with the geometric fast path on the S4D-real init."""
+    inp = scan_inputs(2, 130, 48, seed=7)
+    a = _run(inp, flags=(lpc << 4) | 1)
+    b = _run(inp, flags=(lpc << 4))
+    ref = _oracle(inp)
+    _compare(a, ref, TOL32)
+    _compare(b, ref, TOL32)
+
+
+def test_no_gate():
+    inp = scan_inputs(2, 50, 32, seed=3, random_A=True)
+    res = _run(inp, gate=False)
+    assert "dz" not in res
+    _compare(res, _oracle(inp, gate=False), TOL32)
+
+
+@pytest.mark.parametrize("tag", ["init", "randA", "short"])
+def test_against_reference_goldens(golden, tag):
+    """the committed outputs of the unmodified reference (MambaBlock.selective_scan + gate + autograd)."""
+    g = golden(f"selscan_{tag}")
+    res = _run(g)
+    assert relerr(res["out"], g["out"]) <= TOL32
+    for k in ("dx", "ddelta", "dz", "dA", "dB", "dC", "dD"):
+        assert relerr(res[k], g[k]) <= TOL32, k
+    y = _run(g, gate=False, grad=False)["out"]
+    assert relerr(y, g["y_pscan"]) <= TOL32 and relerr(y, g["y_seq"]) <= TOL32
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, TOL16), (torch.float16, 5e-3)])
+@pytest.mark.parametrize("random_A", [False, True])
+def test_half_io(dtype, tol, random_A):
+    """16-bit I/O, fp32 state: oracle = fp64 maths on the dtype-rounded inputs."""
+    inp = scan_inputs(2, 200, 64, seed=11, random_A=random_A)
+    rnd = {k: (torch.from_numpy(v).to(dtype).float().numpy() if k not in ("A", "D") else v) for k, v in inp.items()}
+    res = _run(rnd, dtype=dtype)
+    _compare(res, _oracle(rnd), tol)
+
+
+def test_strided_views_no_copy():
+    """x / z passed as chunk() views of an in_proj output (row pitch 2*ED), as MambaBlock.forward produces them."""
+    from mmidet_b200 import ops
+    B, L, ED = 2, 70, 32
+    inp = scan_inputs(B, L, ED, seed=5, random_A=True)
+    xz = torch.cat([_t(inp["x"]), _t(inp["z"])], dim=-1)
+    xv, zv = xz.chunk(2, dim=-1)
+    out = ops.selective_scan(xv, _t(inp["delta"]), _t(inp["A"]), _t(inp["Bm"]), _t(inp["Cm"]), _t(inp["D"]), z=zv)
+    assert relerr(out.cpu().numpy(), _oracle(inp, grad=False)["out"]) <= TOL32
+
+
+def test_state_passing_and_checkpoints():
+    """h0 -> hT chaining across two calls equals one call; chk[j] is the state entering step j*chunk."""
+    from mmidet_b200 import ops
+    B, L, ED = 2, 83, 24
+    inp = scan_inputs(B, L, ED, seed=9, random_A=True)
+    a = {k: _t(v) for k, v in inp.items()}
+    full, hT, chk, _ = ops.selscan_fwd_raw(a["x"], a["delta"], a["A"], a["Bm"], a["Cm"], a["D"], z=a["z"],
+                                           want_state=True, want_chk=True)
+    cut = 35
+    o1, h1, _, _ = ops.selscan_fwd_raw(a["x"][:, :cut].contiguous(), a["delta"][:, :cut].contiguous(), a["A"],
+                                       a["Bm"][:, :cut].contiguous(), a["Cm"][:, :cut].contiguous(), a["D"],
+                                       z=a["z"][:, :cut].contiguous(), want_state=True)
+    o2, h2, _, _ = ops.selscan_fwd_raw(a["x"][:, cut:].contiguous(), a["delta"][:, cut:].contiguous(), a["A"],
+                                       a["Bm"][:, cut:].contiguous(), a["Cm"][:, cut:].contiguous(), a["D"],
+                                       z=a["z"][:, cut:].contiguous(), h0=h1, want_state=True)
+    assert relerr(torch.cat([o1, o2], 1).cpu().numpy(), full.cpu().numpy()) <= 1e-5
+    assert relerr(h2.cpu().numpy(), hT.cpu().numpy()) <= 1e-5
+    chunk = ops.selscan_chunk()
+    _, h32 = O.selective_scan_fwd(inp["x"][:, :2 * chunk], inp["delta"][:, :2 * chunk], inp["A"], inp["Bm"][:, :2 * chunk],
+                                  inp["Cm"][:, :2 * chunk], inp["D"], dtype=np.float64, return_state=True)
+    assert relerr(chk[:, 2].cpu().numpy(), h32) <= TOL32
+    assert float(chk[:, 0].abs().max()) == 0.0
+
+
+def test_long_sequence_small_delta():
+    """L=6400 with small delta (long memory, a -> 1): carries across 400 chunks stay within tolerance."""
+    inp = scan_inputs(1, 6400, 16, seed=2, small_delta=True)
+    res = _run(inp)
+    _compare(res, _oracle(inp), TOL32)
+
+
+def test_linearity_in_x_at_full_size():
+    """size-independent property at the BASELINE shape (B=2, L=6400, ED=512): y is linear in x for fixed
+    delta/B/C (models/mamba.py:222-231), and dx equals the adjoint applied to dout."""
+    from mmidet_b200 import ops
+    torch.manual_seed(0)
+    B, L, ED, N = 2, 6400, 512, 16
+    dev = "cuda"
+    x1, x2 = torch.randn(2, B, L, ED, device=dev)
+    delta = torch.nn.functional.softplus(torch.randn(B, L, ED, device=dev) - 3)
+    Bm, Cm = torch.randn(2, B, L, N, device=dev)
+    A = -torch.arange(1, N + 1, device=dev, dtype=torch.float32).repeat(ED, 1)
+    D = torch.ones(ED, device=dev)
+    f = lambda x: ops.selective_scan(x, delta, A, Bm, Cm, D)
+    y1, y2, y12 = f(x1), f(x2), f(x1 + 2 * x2)
+    err = (y12 - (y1 + 2 * y2)).abs().max() / y12.abs().max()
+    assert float(err) <= 1e-4
+    # adjoint identity <f(x1), w> == <x1, f^T(w)>
+    xr = x1.clone().requires_grad_(True)
+    w = torch.randn_like(y1)
+    (gx,) = torch.autograd.grad(f(xr), xr, w)
+    lhs, rhs = (y1.double() * w.double()).sum(), (x1.double() * gx.double()).sum()
+    assert abs(float(lhs - rhs)) <= 1e-4 * abs(float(lhs))
+
+
+def test_errors_are_loud():
+    from mmidet_b200 import ops
+    x = torch.randn(1, 8, 12, device="cuda")  # ED not a multiple of 8
+    with pytest.raises(RuntimeError):
+        ops.selective_scan(x, x, torch.randn(12, 16, device="cuda"), torch.randn(1, 8, 16, device="cuda"),
+                           torch.randn(1, 8, 16, device="cuda"), torch.randn(12, device="cuda"))
+    with pytest.raises(RuntimeError):  # CPU tensors: no fallback
+        ops.selective_scan(torch.randn(1, 8, 16), torch.randn(1, 8, 16), torch.randn(16, 16), torch.randn(1, 8, 16),
+                           torch.randn(1, 8, 16), torch.randn(16))
