@@ -78,10 +78,13 @@ int mmi_selscan_bwd(const void *x, const void *delta, const void *z, const float
  *   A, X, H : (B, L, D, N) fp32 contiguous.  Inputs are not modified (reference clones, pscan.py:167-174).
  * mmi_pscan_bwd replaces PScan.backward (models/pscan.py:189-224): gA[t] = H[t-1]*G[t] (gA[0]=0), gX = G with
  *   G[t] = gH[t] + A[t+1]*G[t+1].
+ * L is split into segments scanned in parallel; `ws` (>= mmi_pscan_ws_bytes bytes) holds the per-segment
+ * (product, local state) summaries that the second pass chains.  Any D, N (only D*N matters).
  * --------------------------------------------------------------------------------------------------------- */
-int mmi_pscan_fwd(const float *A, const float *X, float *H, int B, int L, int D, int N, void *stream);
-int mmi_pscan_bwd(const float *A, const float *H, const float *gH, float *gA, float *gX, int B, int L, int D, int N,
-                  void *stream);
+int64_t mmi_pscan_ws_bytes(int B, int L, int D, int N);
+int mmi_pscan_fwd(const float *A, const float *X, float *H, void *ws, int B, int L, int D, int N, void *stream);
+int mmi_pscan_bwd(const float *A, const float *H, const float *gH, float *gA, float *gX, void *ws, int B, int L, int D,
+                  int N, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Fusion Focus Module Fourier step.  Replaces extract_frequency2 (models/common.py:37-69):
@@ -95,6 +98,9 @@ int mmi_pscan_bwd(const float *A, const float *H, const float *gH, float *gA, fl
  * --------------------------------------------------------------------------------------------------------- */
 int mmi_ffm_extract(const void *img, void *low, void *high, float *high_mul, int BC, int H, int W, int dtype,
                     void *stream);
+/* Host helper: the [start, stop) row/column ranges of the SHIFTED spectrum that the reference's low-pass keeps
+ * (== the block its high-pass zeroes), reproducing Python slice semantics for negative starts. */
+void mmi_ffm_kept_range(int H, int W, int *r0, int *r1, int *c0, int *c1);
 
 /* Separation loss (models/common.py:128-139) in closed form:
  *   sum_{i<j} M_i.M_j / (l(l-1)) = (|sum_i M_i|^2 - sum_i |M_i|^2) / (2 l (l-1)).   M (l, K) fp32 -> loss[0]. */

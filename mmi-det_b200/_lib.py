@@ -61,8 +61,10 @@ _SIGNATURES = {
     "mmi_selscan_fwd": (_i, [_vp] * 11 + [_i] * 4 + [_i64] * 4 + [_i] * 3 + [_vp]),
     "mmi_selscan_bwd_ws_bytes": (_i64, [_i] * 4),
     "mmi_selscan_bwd": (_i, [_vp] * 17 + [_i] * 4 + [_i64] * 4 + [_i] * 3 + [_vp]),
-    "mmi_pscan_fwd": (_i, [_vp] * 3 + [_i] * 4 + [_vp]),
-    "mmi_pscan_bwd": (_i, [_vp] * 5 + [_i] * 4 + [_vp]),
+    "mmi_pscan_ws_bytes": (_i64, [_i] * 4),
+    "mmi_pscan_fwd": (_i, [_vp] * 4 + [_i] * 4 + [_vp]),
+    "mmi_pscan_bwd": (_i, [_vp] * 6 + [_i] * 4 + [_vp]),
+    "mmi_ffm_kept_range": (None, [_i, _i] + [_c.POINTER(_i)] * 4),
     "mmi_ffm_extract": (_i, [_vp] * 4 + [_i] * 4 + [_vp]),
     "mmi_separation_loss": (_i, [_vp] * 2 + [_i] * 2 + [_vp]),
     "mmi_selscan_fwd_bwd_host": (_i, [_vp] * 16 + [_i] * 6),

@@ -77,6 +77,15 @@ static int check_scan_args(const char *who, int B, int L, int ED, int N, int dty
     return MMI_OK;
 }
 
+int pscan_fwd_launch(const float *A, const float *X, float *H, float *ws, int B, int L, int DN, cudaStream_t st);
+int pscan_bwd_launch(const float *A, const float *H, const float *gH, float *gA, float *gX, float *ws, int B, int L, int DN,
+                     cudaStream_t st);
+int64_t pscan_ws_bytes(int B, int L, int D, int N);
+int ffm_extract_launch(const void *img, void *low, void *high, float *high_mul, int BC, int H, int W, int dtype,
+                       cudaStream_t st);
+int separation_loss_launch(const float *M, float *loss, int l, int K, cudaStream_t st);
+void ffm_kept_range(int H, int W, int *r0, int *r1, int *c0, int *c1);
+
 }  // namespace mmi
 
 using namespace mmi;
@@ -147,6 +156,49 @@ int mmi_selscan_bwd(const void *x, const void *delta, const void *z, const float
     p.x_ld = x_ld; p.d_ld = delta_ld; p.z_ld = z_ld; p.g_ld = dout_ld;
     p.flags = flags;
     return selscan_bwd_launch(p, dtype, ws, static_cast<cudaStream_t>(stream));
+}
+
+int64_t mmi_pscan_ws_bytes(int B, int L, int D, int N) {
+    if (B <= 0 || L <= 0 || D <= 0 || N <= 0) return 0;
+    return pscan_ws_bytes(B, L, D, N);
+}
+
+static int check_pscan(const char *who, int B, int L, int D, int N) {
+    if (B <= 0 || L <= 0 || D <= 0 || N <= 0) { set_error("%s: B, L, D, N must be positive", who); return MMI_ERR_ARG; }
+    if (B > 65535) { set_error("%s: B=%d exceeds 65535", who, B); return MMI_ERR_ARG; }
+    if (int64_t(D) * N > (int64_t(1) << 30)) { set_error("%s: D*N too large", who); return MMI_ERR_ARG; }
+    return require_device();
+}
+
+int mmi_pscan_fwd(const float *A, const float *X, float *H, void *ws, int B, int L, int D, int N, void *stream) {
+    if (!A || !X || !H || !ws) { set_error("mmi_pscan_fwd: null pointer"); return MMI_ERR_ARG; }
+    if (int e = check_pscan("mmi_pscan_fwd", B, L, D, N)) return e;
+    return pscan_fwd_launch(A, X, H, static_cast<float *>(ws), B, L, D * N, static_cast<cudaStream_t>(stream));
+}
+
+int mmi_pscan_bwd(const float *A, const float *H, const float *gH, float *gA, float *gX, void *ws, int B, int L, int D,
+                  int N, void *stream) {
+    if (!A || !H || !gH || !gA || !gX || !ws) { set_error("mmi_pscan_bwd: null pointer"); return MMI_ERR_ARG; }
+    if (int e = check_pscan("mmi_pscan_bwd", B, L, D, N)) return e;
+    return pscan_bwd_launch(A, H, gH, gA, gX, static_cast<float *>(ws), B, L, D * N, static_cast<cudaStream_t>(stream));
+}
+
+int mmi_ffm_extract(const void *img, void *low, void *high, float *high_mul, int BC, int H, int W, int dtype,
+                    void *stream) {
+    if (!img || !low || !high) { set_error("mmi_ffm_extract: null pointer"); return MMI_ERR_ARG; }
+    if (BC <= 0) { set_error("mmi_ffm_extract: BC must be positive"); return MMI_ERR_ARG; }
+    if (!elem_size(dtype)) { set_error("mmi_ffm_extract: unknown dtype %d", dtype); return MMI_ERR_ARG; }
+    if (int e = require_device()) return e;
+    return ffm_extract_launch(img, low, high, high_mul, BC, H, W, dtype, static_cast<cudaStream_t>(stream));
+}
+
+void mmi_ffm_kept_range(int H, int W, int *r0, int *r1, int *c0, int *c1) { ffm_kept_range(H, W, r0, r1, c0, c1); }
+
+int mmi_separation_loss(const float *M, float *loss, int l, int K, void *stream) {
+    if (!M || !loss) { set_error("mmi_separation_loss: null pointer"); return MMI_ERR_ARG; }
+    if (l < 2 || K < 1) { set_error("mmi_separation_loss: need l >= 2 rows and K >= 1 columns (l=%d K=%d)", l, K); return MMI_ERR_ARG; }
+    if (int e = require_device()) return e;
+    return separation_loss_launch(M, loss, l, K, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"
