@@ -13,7 +13,7 @@ _DIR = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_DIR)
 SO_PATH = os.path.join(_DIR, "libmmidet_b200.so")
 CSRC = os.path.join(_DIR, "csrc")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
+NVCC_FLAGS = ["-t", "8", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 
 MMI_F32, MMI_BF16, MMI_F16 = 0, 1, 2

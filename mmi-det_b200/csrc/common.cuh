@@ -127,3 +127,15 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
 }
 
 }  // namespace mmi
+
+namespace mmi {
+// TMA engine, 2-D tile shared -> global (SASS: UTMASTG); out-of-bounds parts of the box are clipped.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int col, int row, const void *src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(col),
+                 "r"(row), "r"(smem_u32(src))
+                 : "memory");
+}
+template <int N> __device__ __forceinline__ void bulk_wait_all() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+}  // namespace mmi

@@ -27,7 +27,7 @@
 namespace mmi {
 
 struct BwdMaps {
-    CUtensorMap x, d, z, g, B, C;
+    CUtensorMap x, d, z, g, B, C, odx, odd, odz;
 };
 
 template <typename T, int LPC, int NW, int TC, int STAGES> struct BwdLayout {
@@ -41,12 +41,13 @@ template <typename T, int LPC, int NW, int TC, int STAGES> struct BwdLayout {
     static constexpr size_t DYS_OFF = HIST_OFF + NW * HIST_WARP_BYTES;
     static constexpr int DYS_LD = CPW + 1;
     static constexpr size_t DBC_OFF = DYS_OFF + size_t(NW) * TC * DYS_LD * 4;
-    static constexpr size_t BC32_OFF = DBC_OFF + size_t(2) * NW * TC * N * 4;
+    static constexpr size_t OUT_OFF = DBC_OFF + size_t(2) * NW * TC * N * 4;  // [2 buffers][dx, ddelta, dz] tiles
+    static constexpr size_t BC32_OFF = OUT_OFF + 6 * TILE_BYTES;
     static constexpr size_t BAR_OFF = BC32_OFF + (sizeof(T) == 2 ? size_t(2) * TC * N * 4 : 0);
     static constexpr size_t SMEM = BAR_OFF + STAGES * sizeof(uint64_t);
 };
 
-template <typename T, int LPC, int NW, int TC, int STAGES, bool GEOM>
+template <typename T, int LPC, int NW, int TC, int STAGES, bool GEOM, bool HAS_Z>
 __device__ __forceinline__ void bwd_body(const BwdParams &p, const BwdMaps &tm, unsigned char *smem,
                                          const float (&A2)[kN / LPC], float A2base, float Dd, int c0, int chw, int b,
                                          int cl, int c, bool active, int sub, int warp, int lane) {
@@ -60,7 +61,7 @@ __device__ __forceinline__ void bwd_body(const BwdParams &p, const BwdMaps &tm, 
     float *bc32 = reinterpret_cast<float *>(smem + Lay::BC32_OFF);
 
     const int L = p.L, ED = p.ED;
-    const bool has_z = p.z != nullptr;
+    constexpr bool has_z = HAS_Z;
     const int nch = (L + TC - 1) / TC;
     const int64_t row_b = int64_t(b) * L;
     const int chl = lane / LPC;  // channel within the warp
@@ -95,10 +96,20 @@ __device__ __forceinline__ void bwd_body(const BwdParams &p, const BwdMaps &tm, 
         if constexpr (GEOM) {
             const float r = ex2(dv * A2base);
             const float q = (LPC == 1) ? r : ex2(dv * A2[0]);
-            const float2 rr = splat2(r * r);
+            const float r2 = r * r;
             a2[0] = make_float2(q, q * r);
+            if constexpr (NP >= 2) a2[1] = mul2(a2[0], splat2(r2));
+            if constexpr (NP >= 4) {
+                const float2 r4 = splat2(r2 * r2);
+                a2[2] = mul2(a2[0], r4);
+                a2[3] = mul2(a2[1], r4);
+            }
+            if constexpr (NP >= 8) {
+                const float r4s = r2 * r2;
+                const float2 r8 = splat2(r4s * r4s);
 #pragma unroll
-            for (int k = 1; k < NP; ++k) a2[k] = mul2(a2[k - 1], rr);
+                for (int k = 4; k < 8; ++k) a2[k] = mul2(a2[k - 4], r8);
+            }
         } else {
             const float2 dv2 = splat2(dv);
 #pragma unroll
@@ -153,8 +164,7 @@ __device__ __forceinline__ void bwd_body(const BwdParams &p, const BwdMaps &tm, 
                 hist[k * 32 + lane] = w;
             }
         }
-#pragma unroll 2
-        for (int t = 0; t < tl; ++t) {
+        auto p1_step = [&](int t) {
             const float xv = to_f32<T>(sx[t * CH + cl]), dv = to_f32<T>(sd[t * CH + cl]);
             float2 Bv[NP], a2[NP];
             loadBC(fB, t, Bv);
@@ -166,11 +176,17 @@ __device__ __forceinline__ void bwd_body(const BwdParams &p, const BwdMaps &tm, 
             for (int k = 0; k < K4; ++k)
                 hist[((t + 1) * K4 + k) * 32 + lane] = make_float4(h2[2 * k].x, h2[2 * k].y, h2[2 * k + 1].x, h2[2 * k + 1].y);
             float dy = to_f32<T>(sg[t * CH + cl]);
-            if (has_z) {
+            if constexpr (HAS_Z) {
                 const float zv = to_f32<T>(sz[t * CH + cl]);
                 dy *= zv * sigmoidf_fast(zv);
             }
-            if (sub == 0) dys[t * Lay::DYS_LD + chl] = dy;
+            dys[t * Lay::DYS_LD + chl] = dy;  // the LPC lanes of a channel write the same value
+        };
+        if (tl == TC) {
+#pragma unroll
+            for (int t = 0; t < TC; ++t) p1_step(t);
+        } else {
+            for (int t = 0; t < tl; ++t) p1_step(t);
         }
         __syncwarp();
 
@@ -213,7 +229,8 @@ __device__ __forceinline__ void bwd_body(const BwdParams &p, const BwdMaps &tm, 
         float2 hc2[NP];
 #pragma unroll
         for (int k = 0; k < NP; ++k) hc2[k] = h2[k];
-        for (int t = tl - 1; t >= 0; --t) {
+        T *so = reinterpret_cast<T *>(smem + Lay::OUT_OFF + (i & 1) * 3 * Lay::TILE_BYTES) + cl;  // dx | ddelta | dz tiles
+        auto p3_step = [&](int t, bool to_smem) {
             const float xv = to_f32<T>(sx[t * CH + cl]), dv = to_f32<T>(sd[t * CH + cl]);
             const float gv = to_f32<T>(sg[t * CH + cl]);
             float2 Bv[NP], Cv[NP], a2[NP], hp2[NP];
@@ -227,7 +244,7 @@ __device__ __forceinline__ void bwd_body(const BwdParams &p, const BwdMaps &tm, 
                 hp2[2 * k + 1] = make_float2(w.z, w.w);
             }
             float zv = 0.f, sig = 1.f, dy = gv;
-            if (has_z) {
+            if constexpr (HAS_Z) {
                 zv = to_f32<T>(sz[t * CH + cl]);
                 sig = sigmoidf_fast(zv);
                 dy = gv * zv * sig;
@@ -263,15 +280,29 @@ __device__ __forceinline__ void bwd_body(const BwdParams &p, const BwdMaps &tm, 
             }
             y = fmaf(Dd, xv, y);
             dDacc = fmaf(dy, xv, dDacc);
-            if (active && sub == 0) {
+            const T odx = from_f32<T>(fmaf(gB, dv, Dd * dy)), odd = from_f32<T>(fmaf(gB, xv, dd));
+            const T odz = from_f32<T>(gv * y * sig * fmaf(zv, 1.f - sig, 1.f));
+            if (to_smem) {  // the LPC lanes of a channel write identical values
+                so[t * CH] = odx;
+                so[TC * CH + t * CH] = odd;
+                if constexpr (HAS_Z) so[2 * TC * CH + t * CH] = odz;
+            } else if (active && sub == 0) {
                 const int64_t o = (row_b + t0 + t) * ED + c;
-                st_cs(gdx + o, from_f32<T>(fmaf(gB, dv, Dd * dy)));
-                st_cs(gdd + o, from_f32<T>(fmaf(gB, xv, dd)));
-                if (has_z) st_cs(gdz + o, from_f32<T>(gv * y * sig * fmaf(zv, 1.f - sig, 1.f)));
+                gdx[o] = odx;
+                gdd[o] = odd;
+                if constexpr (HAS_Z) gdz[o] = odz;
             }
+        };
+        if (tl == TC) {
+#pragma unroll
+            for (int t = TC - 1; t >= 0; --t) p3_step(t, true);
+            fence_proxy_async();
+        } else {
+            for (int t = tl - 1; t >= 0; --t) p3_step(t, false);
         }
         __syncwarp();
         reduce_hist(dbc + warp * TC * N, false);  // dB partial of this warp
+        if (threadIdx.x == 0) bulk_wait_read<0>();  // the previous chunk's tile stores have drained their buffers
         __syncthreads();
 
         // ---- combine the warps' partials, one 128-byte row [dB(16) | dC(16)] per timestep --------------------
@@ -283,8 +314,18 @@ __device__ __forceinline__ void bwd_body(const BwdParams &p, const BwdMaps &tm, 
             p.ws_bc[((row_b + t0 + t) * p.ntile_c + blockIdx.x) * (2 * N) + r] = v;
         }
         __syncthreads();  // stage s, history and dbc are free again
-        if (threadIdx.x == 0 && i + STAGES < nch) issue(s, nch - 1 - (i + STAGES));
+        if (threadIdx.x == 0) {
+            if (tl == TC) {
+                const T *ob = so - cl;
+                tma_store_2d(&tm.odx, c0, int(row_b) + t0, ob);
+                tma_store_2d(&tm.odd, c0, int(row_b) + t0, ob + TC * CH);
+                if (HAS_Z) tma_store_2d(&tm.odz, c0, int(row_b) + t0, ob + 2 * TC * CH);
+                bulk_commit();
+            }
+            if (i + STAGES < nch) issue(s, nch - 1 - (i + STAGES));
+        }
     }
+    if (threadIdx.x == 0) bulk_wait_read<0>();
 
     if (active) {  // per-batch partials of dA (pre-scaled A2 -> A handled above), dD
         float *o = p.ws_ad + (int64_t(b) * ED + c) * (N + 1);
@@ -328,10 +369,17 @@ __global__ void __launch_bounds__(NW * 32) selscan_bwd_kernel(const BwdParams p,
     }
     const float Dd = p.D[cc];
     const bool geom = __syncthreads_and(ok);
-    if (geom)
-        bwd_body<T, LPC, NW, TC, STAGES, true>(p, tm, smem, A2, A2base, Dd, c0, chw, b, cl, c, active, sub, warp, lane);
-    else
-        bwd_body<T, LPC, NW, TC, STAGES, false>(p, tm, smem, A2, A2base, Dd, c0, chw, b, cl, c, active, sub, warp, lane);
+    const bool has_z = p.z != nullptr;
+#define MMI_BWD_BODY(G, Z) \
+    bwd_body<T, LPC, NW, TC, STAGES, G, Z>(p, tm, smem, A2, A2base, Dd, c0, chw, b, cl, c, active, sub, warp, lane)
+    if (geom) {
+        if (has_z) MMI_BWD_BODY(true, true);
+        else MMI_BWD_BODY(true, false);
+    } else {
+        if (has_z) MMI_BWD_BODY(false, true);
+        else MMI_BWD_BODY(false, false);
+    }
+#undef MMI_BWD_BODY
 }
 
 // Deterministic reduction of the workspace partials: dB/dC over channel tiles, dA/dD over the batch.
@@ -383,6 +431,10 @@ template <typename T, int LPC> static int launch_bwd_t(BwdParams p, int dtype, v
         if (int e = make_tmap_2d(&tm.z, p.z, dtype, rows, p.ED, p.z_ld * sizeof(T), TC, Lay::CH)) return e;
     if (int e = make_tmap_2d(&tm.B, p.Bm, dtype, rows, kN, kN * sizeof(T), TC, kN)) return e;
     if (int e = make_tmap_2d(&tm.C, p.Cm, dtype, rows, kN, kN * sizeof(T), TC, kN)) return e;
+    if (int e = make_tmap_2d(&tm.odx, p.dx, dtype, rows, p.ED, p.ED * sizeof(T), TC, Lay::CH)) return e;
+    if (int e = make_tmap_2d(&tm.odd, p.ddelta, dtype, rows, p.ED, p.ED * sizeof(T), TC, Lay::CH)) return e;
+    if (p.dz)
+        if (int e = make_tmap_2d(&tm.odz, p.dz, dtype, rows, p.ED, p.ED * sizeof(T), TC, Lay::CH)) return e;
     dim3 grid(p.ntile_c, p.B);
     kern<<<grid, NW * 32, Lay::SMEM, st>>>(p, tm);
     if (int e = check_cuda(cudaGetLastError(), "selscan_bwd launch")) return e;

@@ -11,72 +11,74 @@
 // registers for the whole sequence; a warp owns 32/LPC adjacent channels; a CTA owns NW warps = CH channels of one
 // batch element and walks t = 0..L-1.  Tiles [TC timesteps x CH channels] of x / delta / z and [TC x N] of B / C
 // are staged into shared memory by the TMA engine (cp.async.bulk.tensor 2-D tiles, one mbarrier per stage, a
-// STAGES-deep ring), so
-// HBM latency is covered by bytes in flight, not by thread count.  The recurrence, the C.h readout, the D skip and
-// the gate run on packed fp32x2 (FFMA2).  exp() is MUFU ex2 on delta*A*log2(e); when a channel's A row is geometric,
-// A[d,n] = (n+1) A[d,0] (the S4D-real init of models/mamba.py:158-159, which the reference training loop never
-// updates), a[t,n] = r^(n+1) needs one ex2 per step instead of N (detected on the device, per CTA).
+// STAGES-deep ring), so HBM latency is covered by bytes in flight, not by thread count; the output tile goes back
+// through shared memory and a TMA tile store.  Only h = a*h + u is serial in t: each tile is processed in
+// branch-free, fully unrolled blocks of kBlk steps so that loads, exponentials, the C.h readout, the D skip and the
+// gate of neighbouring steps overlap that one dependent FFMA2 per state pair.  exp() is MUFU ex2 on delta*A*log2(e);
+// when a channel's A row is geometric, A[d,n] = (n+1) A[d,0] (the S4D-real init of models/mamba.py:158-159, which
+// the reference training loop never updates), a[t,n] = r^(n+1) needs one or two ex2 per step
+// instead of N (detected on the device, per CTA; MMI_FLAG_NO_GEOM forces the general path).
 #include <cstring>
+#include <type_traits>
 
+#include "../../include/mmidet_b200.h"
 #include "common.cuh"
 #include "selscan.h"
-#include "../../include/mmidet_b200.h"
 
 namespace mmi {
 
 struct FwdMaps {
-    CUtensorMap x, d, z, B, C;
+    CUtensorMap x, d, z, B, C, o;
 };
+
+constexpr int kBlk = 8;  // steps per branch-free block
 
 template <typename T, int LPC, int NW, int TC, int STAGES> struct FwdLayout {
     static constexpr int N = kN, NS = N / LPC, CPW = 32 / LPC, CH = NW * CPW;
-    static constexpr int STAGE_ELEMS = TC * (3 * CH + 2 * N);
-    static constexpr size_t STAGE_BYTES = size_t(STAGE_ELEMS) * sizeof(T);
-    static constexpr size_t BC32_BYTES = sizeof(T) == 2 ? size_t(2) * TC * N * 4 : 0;
-    static constexpr size_t BAR_OFF = STAGES * STAGE_BYTES + BC32_BYTES;
+    static constexpr size_t TILE_BYTES = size_t(TC) * CH * sizeof(T);
+    static constexpr size_t BCT_BYTES = size_t(TC) * N * sizeof(T);
+    static constexpr size_t STAGE_BYTES = 3 * TILE_BYTES + 2 * BCT_BYTES;
+    static constexpr size_t OUT_OFF = STAGES * STAGE_BYTES;  // 2 output tiles
+    static constexpr size_t BC32_OFF = OUT_OFF + 2 * TILE_BYTES;
+    static constexpr size_t BAR_OFF = BC32_OFF + (sizeof(T) == 2 ? size_t(2) * TC * N * 4 : 0);
     static constexpr size_t SMEM = BAR_OFF + STAGES * sizeof(uint64_t);
 };
 
-template <typename T, int LPC, int NW, int TC, int STAGES, bool GEOM>
+template <typename T, int LPC, int NW, int TC, int STAGES, bool GEOM, bool HAS_Z>
 __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, unsigned char *smem,
-                                         const float (&A2)[kN / LPC],
-                                         float A2base, float Dd, int c0, int chw, int b, int cl, int c, bool active,
-                                         int sub, int warp, int lane) {
+                                         const float (&A2)[kN / LPC], float A2base, float Dd, int c0, int b, int cl, int c,
+                                         bool active, int sub) {
     using Lay = FwdLayout<T, LPC, NW, TC, STAGES>;
     constexpr int N = kN, NS = Lay::NS, CH = Lay::CH, NP = NS / 2;
-    T *stage0 = reinterpret_cast<T *>(smem);
-    float *bc32 = reinterpret_cast<float *>(smem + STAGES * Lay::STAGE_BYTES);
+    float *bc32 = reinterpret_cast<float *>(smem + Lay::BC32_OFF);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + Lay::BAR_OFF);
 
     const int L = p.L, ED = p.ED;
-    const bool has_z = p.z != nullptr;
     const int ntiles = (L + TC - 1) / TC, nchk = (L + kChunk - 1) / kChunk;
     T *gout = static_cast<T *>(p.out);
     const int64_t row_b = int64_t(b) * L;
 
-    auto issue = [&](int s, int ti) {  // one elected lane: 5 TMA tile loads arriving on full[s]
-        T *sx = stage0 + size_t(s) * Lay::STAGE_ELEMS, *sd = sx + TC * CH, *sz = sd + TC * CH, *sB = sz + TC * CH,
-          *sC = sB + TC * N;
+    auto issue = [&](int s, int ti) {  // one elected thread: 5 TMA tile loads arriving on full[s]
+        unsigned char *st = smem + size_t(s) * Lay::STAGE_BYTES;
         const int row0 = int(row_b) + ti * TC;
-        const uint32_t total = uint32_t(TC) * CH * sizeof(T) * (has_z ? 3u : 2u) + 2u * TC * N * sizeof(T);
+        const uint32_t total = uint32_t(Lay::TILE_BYTES) * (HAS_Z ? 3u : 2u) + 2u * uint32_t(Lay::BCT_BYTES);
         mbar_arrive_expect_tx(&full[s], total);
-        tma_load_2d(sx, &tm.x, c0, row0, &full[s]);
-        tma_load_2d(sd, &tm.d, c0, row0, &full[s]);
-        if (has_z) tma_load_2d(sz, &tm.z, c0, row0, &full[s]);
-        tma_load_2d(sB, &tm.B, 0, row0, &full[s]);
-        tma_load_2d(sC, &tm.C, 0, row0, &full[s]);
+        tma_load_2d(st, &tm.x, c0, row0, &full[s]);
+        tma_load_2d(st + Lay::TILE_BYTES, &tm.d, c0, row0, &full[s]);
+        if (HAS_Z) tma_load_2d(st + 2 * Lay::TILE_BYTES, &tm.z, c0, row0, &full[s]);
+        tma_load_2d(st + 3 * Lay::TILE_BYTES, &tm.B, 0, row0, &full[s]);
+        tma_load_2d(st + 3 * Lay::TILE_BYTES + Lay::BCT_BYTES, &tm.C, 0, row0, &full[s]);
     };
 
-    // state
-    float2 h2[NP];
+    float2 h2[NP], A2p[NP];
     {
         const float *h0 = p.h0 ? p.h0 + (int64_t(b) * ED + (active ? c : 0)) * N + sub * NS : nullptr;
 #pragma unroll
-        for (int k = 0; k < NP; ++k) h2[k] = h0 ? make_float2(h0[2 * k], h0[2 * k + 1]) : make_float2(0.f, 0.f);
+        for (int k = 0; k < NP; ++k) {
+            h2[k] = h0 ? make_float2(h0[2 * k], h0[2 * k + 1]) : make_float2(0.f, 0.f);
+            A2p[k] = make_float2(A2[2 * k], A2[2 * k + 1]);
+        }
     }
-    float2 A2p[NP];
-#pragma unroll
-    for (int k = 0; k < NP; ++k) A2p[k] = make_float2(A2[2 * k], A2[2 * k + 1]);
 
     if (threadIdx.x == 0)
         for (int s = 0; s < STAGES && s < ntiles; ++s) issue(s, s);
@@ -84,20 +86,21 @@ __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, 
     for (int it = 0; it < ntiles; ++it) {
         const int s = it % STAGES;
         const int t0 = it * TC, tl = min(TC, L - t0);
-        const T *sx = stage0 + size_t(s) * Lay::STAGE_ELEMS, *sd = sx + TC * CH, *sz = sd + TC * CH, *sB = sz + TC * CH,
-                *sC = sB + TC * N;
+        const unsigned char *st = smem + size_t(s) * Lay::STAGE_BYTES;
+        const T *sx = reinterpret_cast<const T *>(st) + cl, *sd = sx + TC * CH, *sz = sd + TC * CH;
+        const T *sB = reinterpret_cast<const T *>(st + 3 * Lay::TILE_BYTES);
+        T *so = reinterpret_cast<T *>(smem + Lay::OUT_OFF + (it & 1) * Lay::TILE_BYTES) + cl;
         mbar_wait(&full[s], (it / STAGES) & 1);
 
-        const float *fB, *fC;
+        const float *fB;
         if constexpr (sizeof(T) == 2) {  // widen B / C once per CTA instead of once per lane
             for (int i = threadIdx.x; i < 2 * TC * N; i += NW * 32) bc32[i] = to_f32<T>(sB[i]);  // sB, sC contiguous
             __syncthreads();
-            fB = bc32;
-            fC = bc32 + TC * N;
+            fB = bc32 + sub * NS;
         } else {
-            fB = reinterpret_cast<const float *>(sB);
-            fC = reinterpret_cast<const float *>(sC);
+            fB = reinterpret_cast<const float *>(sB) + sub * NS;
         }
+        const float *fC = fB + TC * N;
 
         auto checkpoint = [&](int t) {  // state entering step t0 + t, one per kChunk steps
             if (p.chk && active) {
@@ -108,75 +111,121 @@ __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, 
             }
         };
 
-        auto step = [&](int t) {
-            const float xv = to_f32<T>(sx[t * CH + cl]);
-            const float dv = to_f32<T>(sd[t * CH + cl]);
-            float2 Bv[NP], Cv[NP];
-            {
-                const float4 *bp = reinterpret_cast<const float4 *>(fB + t * N + sub * NS);
-                const float4 *cp = reinterpret_cast<const float4 *>(fC + t * N + sub * NS);
+        // U consecutive timesteps, branch-free and software-pipelined in three phases so that independent work of
+        // neighbouring steps (LDS, MUFU, shuffles, gate) overlaps the serial h chain:
+        //   A  loads + per-step scalars (decay base r, q; delta*x; gate factor z*sigmoid(z))
+        //   B  decay powers, h = a h + u, partial C.h readout          (the only phase that is serial in t)
+        //   C  cross-lane readout sum, D skip, gate -> yv[]
+        auto steps = [&](int tb, auto U_, float(&yv)[kBlk]) {
+            constexpr int U = decltype(U_)::value;
+            float xv[U], dvv[U], rr[U], qq[U], gz[U];
 #pragma unroll
-                for (int k = 0; k < NP / 2; ++k) {
-                    const float4 bb = bp[k], cc = cp[k];
-                    Bv[2 * k] = make_float2(bb.x, bb.y);
-                    Bv[2 * k + 1] = make_float2(bb.z, bb.w);
-                    Cv[2 * k] = make_float2(cc.x, cc.y);
-                    Cv[2 * k + 1] = make_float2(cc.z, cc.w);
+            for (int u = 0; u < U; ++u) {
+                const int t = tb + u;
+                xv[u] = to_f32<T>(sx[t * CH]);
+                dvv[u] = to_f32<T>(sd[t * CH]);
+                if constexpr (GEOM) {
+                    rr[u] = ex2(dvv[u] * A2base);
+                    qq[u] = (LPC == 1) ? rr[u] : ex2(dvv[u] * A2[0]);  // r^(sub*NS + 1)
+                }
+                if constexpr (HAS_Z) {
+                    const float zv = to_f32<T>(sz[t * CH]);
+                    gz[u] = zv * sigmoidf_fast(zv);
                 }
             }
-            float2 a2[NP];
-            if constexpr (GEOM) {
-                const float r = ex2(dv * A2base);
-                const float q = (LPC == 1) ? r : ex2(dv * A2[0]);  // r^(sub*NS + 1)
-                const float2 rr = splat2(r * r);
-                a2[0] = make_float2(q, q * r);
 #pragma unroll
-                for (int k = 1; k < NP; ++k) a2[k] = mul2(a2[k - 1], rr);
-            } else {
-                const float2 dv2 = splat2(dv);
+            for (int u = 0; u < U; ++u) {
+                const int t = tb + u;
+                float2 Bv[NP], Cv[NP];
+                {
+                    const float4 *bp = reinterpret_cast<const float4 *>(fB + t * N);
+                    const float4 *cp = reinterpret_cast<const float4 *>(fC + t * N);
+#pragma unroll
+                    for (int k = 0; k < NP / 2; ++k) {
+                        const float4 bb = bp[k], cc = cp[k];
+                        Bv[2 * k] = make_float2(bb.x, bb.y);
+                        Bv[2 * k + 1] = make_float2(bb.z, bb.w);
+                        Cv[2 * k] = make_float2(cc.x, cc.y);
+                        Cv[2 * k + 1] = make_float2(cc.z, cc.w);
+                    }
+                }
+                float2 a2[NP];
+                if constexpr (GEOM) {
+                    const float r = rr[u], q = qq[u], r2 = r * r;
+                    a2[0] = make_float2(q, q * r);
+                    if constexpr (NP >= 2) a2[1] = mul2(a2[0], splat2(r2));
+                    if constexpr (NP >= 4) {
+                        const float2 r4 = splat2(r2 * r2);
+                        a2[2] = mul2(a2[0], r4);
+                        a2[3] = mul2(a2[1], r4);
+                    }
+                    if constexpr (NP >= 8) {
+                        const float r4s = r2 * r2;
+                        const float2 r8 = splat2(r4s * r4s);
+#pragma unroll
+                        for (int k = 4; k < 8; ++k) a2[k] = mul2(a2[k - 4], r8);
+                    }
+                } else {
+                    const float2 dv2 = splat2(dvv[u]);
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) {
+                        const float2 e = mul2(dv2, A2p[k]);
+                        a2[k] = make_float2(ex2(e.x), ex2(e.y));
+                    }
+                }
+                const float2 dx2 = splat2(dvv[u] * xv[u]);
+                float2 ya = make_float2(0.f, 0.f), yb = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int k = 0; k < NP; ++k) {
-                    const float2 e = mul2(dv2, A2p[k]);
-                    a2[k] = make_float2(ex2(e.x), ex2(e.y));
+                    h2[k] = fma2(a2[k], h2[k], mul2(dx2, Bv[k]));
+                    if (k & 1) yb = fma2(Cv[k], h2[k], yb);
+                    else ya = fma2(Cv[k], h2[k], ya);
                 }
+                ya = add2(ya, yb);
+                yv[u] = ya.x + ya.y;
             }
-            const float2 dx2 = splat2(dv * xv);
-            float2 ya = make_float2(0.f, 0.f), yb = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int k = 0; k < NP; ++k) {
-                h2[k] = fma2(a2[k], h2[k], mul2(dx2, Bv[k]));
-                if (k & 1) yb = fma2(Cv[k], h2[k], yb);
-                else ya = fma2(Cv[k], h2[k], ya);
+            for (int u = 0; u < U; ++u) {
+                float y = yv[u];
+                if constexpr (LPC >= 2) y += __shfl_xor_sync(0xffffffffu, y, 1);
+                if constexpr (LPC >= 4) y += __shfl_xor_sync(0xffffffffu, y, 2);
+                y = fmaf(Dd, xv[u], y);
+                if constexpr (HAS_Z) y *= gz[u];
+                yv[u] = y;
             }
-            ya = add2(ya, yb);
-            float y = ya.x + ya.y;
-            if constexpr (LPC >= 2) y += __shfl_xor_sync(0xffffffffu, y, 1);
-            if constexpr (LPC >= 4) y += __shfl_xor_sync(0xffffffffu, y, 2);
-            y = fmaf(Dd, xv, y);
-            if (has_z) {
-                const float zv = to_f32<T>(sz[t * CH + cl]);
-                y *= zv * sigmoidf_fast(zv);
-            }
-            if (active && sub == 0) st_cs(gout + (row_b + t0 + t) * p.o_ld + c, from_f32<T>(y));
         };
 
-        if (tl == TC) {
+        if (tl == TC) {  // full tile: unrolled blocks, output through shared memory + TMA store
 #pragma unroll
             for (int tc = 0; tc < TC; tc += kChunk) {
                 checkpoint(tc);
-#pragma unroll 4
-                for (int t = tc; t < tc + kChunk; ++t) step(t);
+#pragma unroll 1
+                for (int tb = tc; tb < tc + kChunk; tb += kBlk) {
+                    float yv[kBlk];
+                    steps(tb, std::integral_constant<int, kBlk>{}, yv);
+#pragma unroll
+                    for (int u = 0; u < kBlk; ++u) so[(tb + u) * CH] = from_f32<T>(yv[u]);  // LPC lanes write the same value
+                }
             }
-        } else {
+            fence_proxy_async();  // make the generic-proxy writes of `so` visible to the TMA engine
+            if (threadIdx.x == 0) bulk_wait_read<0>();  // tile it-1's store has finished reading its buffer
+            __syncthreads();  // every warp is done with stage s, bc32 and the out tile
+            if (threadIdx.x == 0) {
+                tma_store_2d(&tm.o, c0, int(row_b) + t0, so - cl);
+                bulk_commit();
+            }
+        } else {  // ragged last tile: direct stores (a box store would spill into the next batch's rows)
             for (int t = 0; t < tl; ++t) {
                 if (t % kChunk == 0) checkpoint(t);
-                step(t);
+                float yv[kBlk];
+                steps(t, std::integral_constant<int, 1>{}, yv);
+                if (active && sub == 0) gout[(row_b + t0 + t) * p.o_ld + c] = from_f32<T>(yv[0]);
             }
+            __syncthreads();
         }
-
-        __syncthreads();  // every warp is done with stage s (and bc32)
         if (threadIdx.x == 0 && it + STAGES < ntiles) issue(s, it + STAGES);
     }
+    if (threadIdx.x == 0) bulk_wait_read<0>();  // shared memory must outlive the last tile store's reads
 
     if (p.hT && active) {
         float *hT = p.hT + (int64_t(b) * ED + c) * N + sub * NS;
@@ -198,7 +247,6 @@ __global__ void __launch_bounds__(NW * 32)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y, c0 = blockIdx.x * CH;
-    const int chw = min(CH, p.ED - c0);
     const int sub = lane % LPC;
     const int cl = warp * CPW + lane / LPC;
     const int c = c0 + cl;
@@ -222,11 +270,17 @@ __global__ void __launch_bounds__(NW * 32)
     }
     const float Dd = p.D[cc];
     const bool geom = __syncthreads_and(ok);  // also publishes the mbarrier inits
+    const bool has_z = p.z != nullptr;
 
-    if (geom)
-        fwd_body<T, LPC, NW, TC, STAGES, true>(p, tm, smem, A2, A2base, Dd, c0, chw, b, cl, c, active, sub, warp, lane);
-    else
-        fwd_body<T, LPC, NW, TC, STAGES, false>(p, tm, smem, A2, A2base, Dd, c0, chw, b, cl, c, active, sub, warp, lane);
+#define MMI_FWD_BODY(G, Z) fwd_body<T, LPC, NW, TC, STAGES, G, Z>(p, tm, smem, A2, A2base, Dd, c0, b, cl, c, active, sub)
+    if (geom) {
+        if (has_z) MMI_FWD_BODY(true, true);
+        else MMI_FWD_BODY(true, false);
+    } else {
+        if (has_z) MMI_FWD_BODY(false, true);
+        else MMI_FWD_BODY(false, false);
+    }
+#undef MMI_FWD_BODY
 }
 
 template <typename T, int LPC> static int launch_fwd_t(const FwdParams &p, int dtype, cudaStream_t st) {
@@ -245,6 +299,7 @@ template <typename T, int LPC> static int launch_fwd_t(const FwdParams &p, int d
         if (int e = make_tmap_2d(&tm.z, p.z, dtype, rows, p.ED, p.z_ld * sizeof(T), TC, Lay::CH)) return e;
     if (int e = make_tmap_2d(&tm.B, p.Bm, dtype, rows, kN, kN * sizeof(T), TC, kN)) return e;
     if (int e = make_tmap_2d(&tm.C, p.Cm, dtype, rows, kN, kN * sizeof(T), TC, kN)) return e;
+    if (int e = make_tmap_2d(&tm.o, p.out, dtype, rows, p.ED, p.o_ld * sizeof(T), TC, Lay::CH)) return e;
     dim3 grid((p.ED + Lay::CH - 1) / Lay::CH, p.B);
     kern<<<grid, NW * 32, Lay::SMEM, st>>>(p, tm);
     return check_cuda(cudaGetLastError(), "selscan_fwd launch");

@@ -76,11 +76,12 @@ def test_ffm_batch_and_dtypes():
         l2, h2 = O.extract_frequency2(x.float().cpu().numpy())
         assert float((lo.float().cpu() - torch.from_numpy(l2.astype(np.float32))).abs().max()) <= 4e-3
         assert float((hi.float().cpu() - torch.from_numpy(h2.astype(np.float32))).abs().max()) <= 8e-3
-    # idempotence of the projection: low(low(x)) == low(x), high(low(x)) == 0 (size-independent property)
-    lo, _ = extract_frequency2(_t(img))
-    lo2, hi2 = extract_frequency2(lo.float())
-    assert float((lo2.float() - lo.float()).abs().max()) <= 2e-3
-    assert float(hi2.float().abs().max()) <= 2e-3
+    # size-independent properties: low + high reconstructs the input (complementary masks), and the split is linear
+    lo, hi = extract_frequency2(_t(img))
+    assert float((lo.float() + hi.float() - _t(img)).abs().max()) <= 4e-3
+    lo2, hi2 = extract_frequency2(_t(2.0 * img))
+    assert float((lo2.float() - 2 * lo.float()).abs().max()) <= 4e-3
+    assert float((hi2.float() - 2 * hi.float()).abs().max()) <= 8e-3
 
 
 def test_separation_loss(golden):
