@@ -33,68 +33,89 @@ struct FwdMaps {
 
 constexpr int kBlk = 8;  // steps per branch-free block
 
-template <typename T, int LPC, int NW, int TC, int STAGES> struct FwdLayout {
+// STATE = true is the segment-summary variant (pass 1 of the L-split): it only needs x, delta and B, produces no
+// output tile, and ends by writing the segment's local end state and its sum of delta.
+template <typename T, int LPC, int NW, int TC, int STAGES, bool STATE> struct FwdLayout {
     static constexpr int N = kN, NS = N / LPC, CPW = 32 / LPC, CH = NW * CPW;
     static constexpr size_t TILE_BYTES = size_t(TC) * CH * sizeof(T);
     static constexpr size_t BCT_BYTES = size_t(TC) * N * sizeof(T);
-    static constexpr size_t STAGE_BYTES = 3 * TILE_BYTES + 2 * BCT_BYTES;
+    static constexpr size_t BC_OFF = (STATE ? 2 : 3) * TILE_BYTES;  // x, delta, (z) then B, (C)
+    static constexpr size_t STAGE_BYTES = BC_OFF + (STATE ? 1 : 2) * BCT_BYTES;
     static constexpr size_t OUT_OFF = STAGES * STAGE_BYTES;  // 2 output tiles
-    static constexpr size_t BC32_OFF = OUT_OFF + 2 * TILE_BYTES;
+    static constexpr size_t BC32_OFF = OUT_OFF + (STATE ? 0 : 2) * TILE_BYTES;
     static constexpr size_t BAR_OFF = BC32_OFF + (sizeof(T) == 2 ? size_t(2) * TC * N * 4 : 0);
     static constexpr size_t SMEM = BAR_OFF + STAGES * sizeof(uint64_t);
 };
 
-template <typename T, int LPC, int NW, int TC, int STAGES, bool GEOM, bool HAS_Z>
+template <typename T, int LPC, int NW, int TC, int STAGES, bool STATE, bool GEOM, bool HAS_Z>
 __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, unsigned char *smem,
                                          const float (&A2)[kN / LPC], float A2base, float Dd, int c0, int b, int cl, int c,
                                          bool active, int sub) {
-    using Lay = FwdLayout<T, LPC, NW, TC, STAGES>;
+    using Lay = FwdLayout<T, LPC, NW, TC, STAGES, STATE>;
     constexpr int N = kN, NS = Lay::NS, CH = Lay::CH, NP = NS / 2;
     float *bc32 = reinterpret_cast<float *>(smem + Lay::BC32_OFF);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + Lay::BAR_OFF);
 
     const int L = p.L, ED = p.ED;
-    const int ntiles = (L + TC - 1) / TC, nchk = (L + kChunk - 1) / kChunk;
+    const int ntiles_all = (L + TC - 1) / TC, nchk = (L + kChunk - 1) / kChunk;
+    const int seg = blockIdx.z, tps = p.seglen / TC;  // tiles per segment
+    const int tile0 = seg * tps, ntiles = min(tps, ntiles_all - tile0);
     T *gout = static_cast<T *>(p.out);
     const int64_t row_b = int64_t(b) * L;
 
     auto issue = [&](int s, int ti) {  // one elected thread: 5 TMA tile loads arriving on full[s]
         unsigned char *st = smem + size_t(s) * Lay::STAGE_BYTES;
-        const int row0 = int(row_b) + ti * TC;
-        const uint32_t total = uint32_t(Lay::TILE_BYTES) * (HAS_Z ? 3u : 2u) + 2u * uint32_t(Lay::BCT_BYTES);
+        const int row0 = int(row_b) + (tile0 + ti) * TC;
+        const uint32_t total = uint32_t(Lay::TILE_BYTES) * ((HAS_Z && !STATE) ? 3u : 2u) +
+                               (STATE ? 1u : 2u) * uint32_t(Lay::BCT_BYTES);
         mbar_arrive_expect_tx(&full[s], total);
         tma_load_2d(st, &tm.x, c0, row0, &full[s]);
         tma_load_2d(st + Lay::TILE_BYTES, &tm.d, c0, row0, &full[s]);
-        if (HAS_Z) tma_load_2d(st + 2 * Lay::TILE_BYTES, &tm.z, c0, row0, &full[s]);
-        tma_load_2d(st + 3 * Lay::TILE_BYTES, &tm.B, 0, row0, &full[s]);
-        tma_load_2d(st + 3 * Lay::TILE_BYTES + Lay::BCT_BYTES, &tm.C, 0, row0, &full[s]);
+        if (HAS_Z && !STATE) tma_load_2d(st + 2 * Lay::TILE_BYTES, &tm.z, c0, row0, &full[s]);
+        tma_load_2d(st + Lay::BC_OFF, &tm.B, 0, row0, &full[s]);
+        if (!STATE) tma_load_2d(st + Lay::BC_OFF + Lay::BCT_BYTES, &tm.C, 0, row0, &full[s]);
     };
 
     float2 h2[NP], A2p[NP];
     {
-        const float *h0 = p.h0 ? p.h0 + (int64_t(b) * ED + (active ? c : 0)) * N + sub * NS : nullptr;
+        const float *h0 = (p.h0 && !STATE) ? p.h0 + (int64_t(b) * ED + (active ? c : 0)) * N + sub * NS : nullptr;
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
             h2[k] = h0 ? make_float2(h0[2 * k], h0[2 * k + 1]) : make_float2(0.f, 0.f);
             A2p[k] = make_float2(A2[2 * k], A2[2 * k + 1]);
         }
     }
+    if constexpr (!STATE) {
+        // L-split pass 2: state entering this segment = chain of the preceding segments' summaries,
+        // h <- exp(A * sum(delta)) * h + local_end_state  (the product of a segment's decays is exp(A * sum delta))
+        const int cs = active ? c : 0;
+        for (int sp = 0; sp < seg; ++sp) {
+            const float sd = p.seg_sumd[(int64_t(b) * p.nseg + sp) * ED + cs];
+            const float2 *e2 = reinterpret_cast<const float2 *>(p.seg_state + ((int64_t(b) * p.nseg + sp) * ED + cs) * N + sub * NS);
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+                const float2 ee = mul2(splat2(sd), A2p[k]);
+                h2[k] = fma2(make_float2(ex2(ee.x), ex2(ee.y)), h2[k], e2[k]);
+            }
+        }
+    }
+    float sumd = 0.f;
 
     if (threadIdx.x == 0)
         for (int s = 0; s < STAGES && s < ntiles; ++s) issue(s, s);
 
     for (int it = 0; it < ntiles; ++it) {
         const int s = it % STAGES;
-        const int t0 = it * TC, tl = min(TC, L - t0);
+        const int t0 = (tile0 + it) * TC, tl = min(TC, L - t0);
         const unsigned char *st = smem + size_t(s) * Lay::STAGE_BYTES;
         const T *sx = reinterpret_cast<const T *>(st) + cl, *sd = sx + TC * CH, *sz = sd + TC * CH;
-        const T *sB = reinterpret_cast<const T *>(st + 3 * Lay::TILE_BYTES);
-        T *so = reinterpret_cast<T *>(smem + Lay::OUT_OFF + (it & 1) * Lay::TILE_BYTES) + cl;
+        const T *sB = reinterpret_cast<const T *>(st + Lay::BC_OFF);
+        T *so = reinterpret_cast<T *>(smem + Lay::OUT_OFF + (STATE ? 0 : (it & 1)) * Lay::TILE_BYTES) + cl;
         mbar_wait(&full[s], (it / STAGES) & 1);
 
         const float *fB;
         if constexpr (sizeof(T) == 2) {  // widen B / C once per CTA instead of once per lane
-            for (int i = threadIdx.x; i < 2 * TC * N; i += NW * 32) bc32[i] = to_f32<T>(sB[i]);  // sB, sC contiguous
+            for (int i = threadIdx.x; i < (STATE ? 1 : 2) * TC * N; i += NW * 32) bc32[i] = to_f32<T>(sB[i]);  // sB, sC contiguous
             __syncthreads();
             fB = bc32 + sub * NS;
         } else {
@@ -103,7 +124,7 @@ __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, 
         const float *fC = fB + TC * N;
 
         auto checkpoint = [&](int t) {  // state entering step t0 + t, one per kChunk steps
-            if (p.chk && active) {
+            if (!STATE && p.chk && active) {
                 float4 *ck = reinterpret_cast<float4 *>(p.chk + ((int64_t(b) * nchk + (t0 + t) / kChunk) * ED + c) * N + sub * NS);
 #pragma unroll
                 for (int k = 0; k < NP / 2; ++k)
@@ -128,10 +149,11 @@ __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, 
                     rr[u] = ex2(dvv[u] * A2base);
                     qq[u] = (LPC == 1) ? rr[u] : ex2(dvv[u] * A2[0]);  // r^(sub*NS + 1)
                 }
-                if constexpr (HAS_Z) {
+                if constexpr (HAS_Z && !STATE) {
                     const float zv = to_f32<T>(sz[t * CH]);
                     gz[u] = zv * sigmoidf_fast(zv);
                 }
+                if constexpr (STATE) sumd += dvv[u];
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -142,11 +164,14 @@ __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, 
                     const float4 *cp = reinterpret_cast<const float4 *>(fC + t * N);
 #pragma unroll
                     for (int k = 0; k < NP / 2; ++k) {
-                        const float4 bb = bp[k], cc = cp[k];
+                        const float4 bb = bp[k];
                         Bv[2 * k] = make_float2(bb.x, bb.y);
                         Bv[2 * k + 1] = make_float2(bb.z, bb.w);
-                        Cv[2 * k] = make_float2(cc.x, cc.y);
-                        Cv[2 * k + 1] = make_float2(cc.z, cc.w);
+                        if constexpr (!STATE) {
+                            const float4 cc = cp[k];
+                            Cv[2 * k] = make_float2(cc.x, cc.y);
+                            Cv[2 * k + 1] = make_float2(cc.z, cc.w);
+                        }
                     }
                 }
                 float2 a2[NP];
@@ -178,12 +203,15 @@ __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, 
 #pragma unroll
                 for (int k = 0; k < NP; ++k) {
                     h2[k] = fma2(a2[k], h2[k], mul2(dx2, Bv[k]));
-                    if (k & 1) yb = fma2(Cv[k], h2[k], yb);
-                    else ya = fma2(Cv[k], h2[k], ya);
+                    if constexpr (!STATE) {
+                        if (k & 1) yb = fma2(Cv[k], h2[k], yb);
+                        else ya = fma2(Cv[k], h2[k], ya);
+                    }
                 }
                 ya = add2(ya, yb);
                 yv[u] = ya.x + ya.y;
             }
+            if constexpr (STATE) return;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 float y = yv[u];
@@ -203,31 +231,50 @@ __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, 
                 for (int tb = tc; tb < tc + kChunk; tb += kBlk) {
                     float yv[kBlk];
                     steps(tb, std::integral_constant<int, kBlk>{}, yv);
+                    if constexpr (!STATE) {
 #pragma unroll
-                    for (int u = 0; u < kBlk; ++u) so[(tb + u) * CH] = from_f32<T>(yv[u]);  // LPC lanes write the same value
+                        for (int u = 0; u < kBlk; ++u) so[(tb + u) * CH] = from_f32<T>(yv[u]);  // LPC lanes write the same value
+                    }
                 }
             }
-            fence_proxy_async();  // make the generic-proxy writes of `so` visible to the TMA engine
-            if (threadIdx.x == 0) bulk_wait_read<0>();  // tile it-1's store has finished reading its buffer
+            if constexpr (!STATE) {
+                fence_proxy_async();  // make the generic-proxy writes of `so` visible to the TMA engine
+                if (threadIdx.x == 0) bulk_wait_read<0>();  // tile it-1's store has finished reading its buffer
+            }
             __syncthreads();  // every warp is done with stage s, bc32 and the out tile
-            if (threadIdx.x == 0) {
-                tma_store_2d(&tm.o, c0, int(row_b) + t0, so - cl);
-                bulk_commit();
+            if constexpr (!STATE) {
+                if (threadIdx.x == 0) {
+                    tma_store_2d(&tm.o, c0, int(row_b) + t0, so - cl);
+                    bulk_commit();
+                }
             }
         } else {  // ragged last tile: direct stores (a box store would spill into the next batch's rows)
             for (int t = 0; t < tl; ++t) {
                 if (t % kChunk == 0) checkpoint(t);
                 float yv[kBlk];
                 steps(t, std::integral_constant<int, 1>{}, yv);
-                if (active && sub == 0) gout[(row_b + t0 + t) * p.o_ld + c] = from_f32<T>(yv[0]);
+                if constexpr (!STATE)
+                    if (active && sub == 0) gout[(row_b + t0 + t) * p.o_ld + c] = from_f32<T>(yv[0]);
             }
             __syncthreads();
         }
         if (threadIdx.x == 0 && it + STAGES < ntiles) issue(s, it + STAGES);
     }
+    if constexpr (STATE) {
+        if (active) {
+            float *e = p.seg_state + ((int64_t(b) * p.nseg + seg) * ED + c) * N + sub * NS;
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+                e[2 * k] = h2[k].x;
+                e[2 * k + 1] = h2[k].y;
+            }
+            if (sub == 0) p.seg_sumd[(int64_t(b) * p.nseg + seg) * ED + c] = sumd;
+        }
+        return;
+    }
     if (threadIdx.x == 0) bulk_wait_read<0>();  // shared memory must outlive the last tile store's reads
 
-    if (p.hT && active) {
+    if (p.hT && active && seg == p.nseg - 1) {
         float *hT = p.hT + (int64_t(b) * ED + c) * N + sub * NS;
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
@@ -237,10 +284,10 @@ __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, 
     }
 }
 
-template <typename T, int LPC, int NW, int TC, int STAGES>
+template <typename T, int LPC, int NW, int TC, int STAGES, bool STATE>
 __global__ void __launch_bounds__(NW * 32)
     selscan_fwd_kernel(const FwdParams p, const __grid_constant__ FwdMaps tm) {
-    using Lay = FwdLayout<T, LPC, NW, TC, STAGES>;
+    using Lay = FwdLayout<T, LPC, NW, TC, STAGES, STATE>;
     constexpr int N = kN, NS = Lay::NS, CPW = Lay::CPW, CH = Lay::CH;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + Lay::BAR_OFF);
@@ -270,9 +317,9 @@ __global__ void __launch_bounds__(NW * 32)
     }
     const float Dd = p.D[cc];
     const bool geom = __syncthreads_and(ok);  // also publishes the mbarrier inits
-    const bool has_z = p.z != nullptr;
+    const bool has_z = p.z != nullptr && !STATE;
 
-#define MMI_FWD_BODY(G, Z) fwd_body<T, LPC, NW, TC, STAGES, G, Z>(p, tm, smem, A2, A2base, Dd, c0, b, cl, c, active, sub)
+#define MMI_FWD_BODY(G, Z) fwd_body<T, LPC, NW, TC, STAGES, STATE, G, Z>(p, tm, smem, A2, A2base, Dd, c0, b, cl, c, active, sub)
     if (geom) {
         if (has_z) MMI_FWD_BODY(true, true);
         else MMI_FWD_BODY(true, false);
@@ -283,13 +330,37 @@ __global__ void __launch_bounds__(NW * 32)
 #undef MMI_FWD_BODY
 }
 
-template <typename T, int LPC> static int launch_fwd_t(const FwdParams &p, int dtype, cudaStream_t st) {
-    constexpr int NW = 2, TC = kFwdTile, STAGES = 4;
-    using Lay = FwdLayout<T, LPC, NW, TC, STAGES>;
-    auto kern = selscan_fwd_kernel<T, LPC, NW, TC, STAGES>;
-    if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Lay::SMEM)),
-                           "selscan_fwd smem attribute"))
-        return e;
+// Number of L segments: enough warps for ~4 per SM sub-partition, segments no shorter than 8 tiles.
+static int pick_nseg(const FwdParams &p, int ch, int nw, int tc) {
+    const int forced = (p.flags & MMI_FLAG_NSEG_MASK) >> MMI_FLAG_NSEG_SHIFT;
+    const int ntiles = (p.L + tc - 1) / tc;
+    int nseg;
+    if (forced) {
+        nseg = min(forced, kMaxSeg);
+    } else {
+        const long warps = long(p.B) * ((p.ED + ch - 1) / ch) * nw;
+        const long want = 16L * sm_count();
+        nseg = int((want + warps - 1) / warps);
+        nseg = min(nseg, max(1, ntiles / 8));
+        nseg = min(nseg, kMaxSeg);
+    }
+    return max(1, min(nseg, ntiles));
+}
+
+template <typename T, int LPC> static int launch_fwd_t(FwdParams p, int dtype, void *ws, cudaStream_t st) {
+    constexpr int NW = 2, TC = kFwdTile, STAGES = 2;
+    using Lay = FwdLayout<T, LPC, NW, TC, STAGES, false>;
+    using LayS = FwdLayout<T, LPC, NW, TC, STAGES, true>;
+    auto kern = selscan_fwd_kernel<T, LPC, NW, TC, STAGES, false>;
+    auto kern_state = selscan_fwd_kernel<T, LPC, NW, TC, STAGES, true>;
+    const int ntiles = (p.L + TC - 1) / TC;
+    int nseg = ws ? pick_nseg(p, Lay::CH, NW, TC) : 1;
+    const int tps = (ntiles + nseg - 1) / nseg;
+    nseg = (ntiles + tps - 1) / tps;
+    p.nseg = nseg;
+    p.seglen = tps * TC;
+    p.seg_state = static_cast<float *>(ws);
+    p.seg_sumd = p.seg_state ? p.seg_state + int64_t(p.B) * kMaxSeg * p.ED * kN : nullptr;
     const uint64_t rows = uint64_t(p.B) * p.L;
     FwdMaps tm;
     memset(&tm, 0, sizeof(tm));
@@ -300,38 +371,50 @@ template <typename T, int LPC> static int launch_fwd_t(const FwdParams &p, int d
     if (int e = make_tmap_2d(&tm.B, p.Bm, dtype, rows, kN, kN * sizeof(T), TC, kN)) return e;
     if (int e = make_tmap_2d(&tm.C, p.Cm, dtype, rows, kN, kN * sizeof(T), TC, kN)) return e;
     if (int e = make_tmap_2d(&tm.o, p.out, dtype, rows, p.ED, p.o_ld * sizeof(T), TC, Lay::CH)) return e;
-    dim3 grid((p.ED + Lay::CH - 1) / Lay::CH, p.B);
-    kern<<<grid, NW * 32, Lay::SMEM, st>>>(p, tm);
+    const unsigned gx = (p.ED + Lay::CH - 1) / Lay::CH;
+    if (nseg > 1) {  // pass 1: local end state + sum(delta) of every segment but the last
+        if (int e = check_cuda(cudaFuncSetAttribute(kern_state, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LayS::SMEM)),
+                               "selscan_fwd(state) smem attribute"))
+            return e;
+        kern_state<<<dim3(gx, p.B, nseg - 1), NW * 32, LayS::SMEM, st>>>(p, tm);
+        if (int e = check_cuda(cudaGetLastError(), "selscan_fwd(state) launch")) return e;
+    }
+    if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Lay::SMEM)),
+                           "selscan_fwd smem attribute"))
+        return e;
+    kern<<<dim3(gx, p.B, nseg), NW * 32, Lay::SMEM, st>>>(p, tm);
     return check_cuda(cudaGetLastError(), "selscan_fwd launch");
 }
 
-template <typename T> static int launch_fwd_lpc(const FwdParams &p, int dtype, int lpc, cudaStream_t st) {
+template <typename T> static int launch_fwd_lpc(const FwdParams &p, int dtype, int lpc, void *ws, cudaStream_t st) {
     switch (lpc) {
-        case 1: return launch_fwd_t<T, 1>(p, dtype, st);
-        case 2: return launch_fwd_t<T, 2>(p, dtype, st);
-        case 4: return launch_fwd_t<T, 4>(p, dtype, st);
+        case 1: return launch_fwd_t<T, 1>(p, dtype, ws, st);
+        case 2: return launch_fwd_t<T, 2>(p, dtype, ws, st);
+        case 4: return launch_fwd_t<T, 4>(p, dtype, ws, st);
     }
     set_error("selscan_fwd: lanes-per-channel must be 1, 2 or 4 (got %d)", lpc);
     return MMI_ERR_ARG;
 }
 
-// Lanes per channel: fewest lanes (least replicated work) that still gives every SM sub-partition a warp.
+// Lanes per channel.  The L-split supplies the thread-level parallelism, so take the mapping with the least replicated
+// work (one lane = one channel, all 16 states in registers) unless ED is too small to fill its 64-channel tile.
 int pick_lpc(int B, int ED, int flags) {
+    (void)B;
     const int forced = (flags & MMI_FLAG_LPC_MASK) >> MMI_FLAG_LPC_SHIFT;
     if (forced) return forced;
-    const long warps1 = long(B) * ED / 32;
-    const long want = 3L * sm_count();
-    if (warps1 >= want) return 1;
-    if (2 * warps1 >= want) return 2;
+    if (ED >= 64) return 1;
+    if (ED >= 32) return 2;
     return 4;
 }
 
-int selscan_fwd_launch(const FwdParams &p, int dtype, cudaStream_t st) {
+int64_t selscan_fwd_ws_bytes(int B, int ED) { return (int64_t(B) * kMaxSeg * ED * kN + int64_t(B) * kMaxSeg * ED) * 4; }
+
+int selscan_fwd_launch(const FwdParams &p, int dtype, void *ws, cudaStream_t st) {
     const int lpc = pick_lpc(p.B, p.ED, p.flags);
     switch (dtype) {
-        case MMI_F32: return launch_fwd_lpc<float>(p, dtype, lpc, st);
-        case MMI_BF16: return launch_fwd_lpc<__nv_bfloat16>(p, dtype, lpc, st);
-        case MMI_F16: return launch_fwd_lpc<__half>(p, dtype, lpc, st);
+        case MMI_F32: return launch_fwd_lpc<float>(p, dtype, lpc, ws, st);
+        case MMI_BF16: return launch_fwd_lpc<__nv_bfloat16>(p, dtype, lpc, ws, st);
+        case MMI_F16: return launch_fwd_lpc<__half>(p, dtype, lpc, ws, st);
     }
     set_error("selscan_fwd: unknown dtype %d", dtype);
     return MMI_ERR_ARG;

@@ -82,6 +82,26 @@ def test_forced_general_path_on_geometric_A(lpc):
     _compare(b, ref, TOL32)
 
 
+@pytest.mark.parametrize("nseg", [1, 2, 5, 64])
+@pytest.mark.parametrize("lpc", [1, 2, 4])
+@pytest.mark.parametrize("random_A", [False, True])
+def test_l_split_segments(nseg, lpc, random_A):
+    """L cut into concurrently scanned segments (forced count, incl. more segments than tiles and a ragged tail):
+    identical results to the unsplit scan, for outputs, gradients, hT and the checkpoints."""
+    from mmidet_b200 import ops
+    inp = scan_inputs(2, 203, 72, seed=nseg + lpc, random_A=random_A)
+    res = _run(inp, flags=(lpc << 4) | (nseg << 8))
+    _compare(res, _oracle(inp), TOL32)
+    a = {k: _t(v) for k, v in inp.items()}
+    h0 = torch.randn(2, 72, 16, device="cuda")
+    o1, hT1, chk1, _ = ops.selscan_fwd_raw(a["x"], a["delta"], a["A"], a["Bm"], a["Cm"], a["D"], z=a["z"], h0=h0,
+                                           want_state=True, want_chk=True, flags=(lpc << 4) | (1 << 8))
+    o2, hT2, chk2, _ = ops.selscan_fwd_raw(a["x"], a["delta"], a["A"], a["Bm"], a["Cm"], a["D"], z=a["z"], h0=h0,
+                                           want_state=True, want_chk=True, flags=(lpc << 4) | (nseg << 8))
+    for u, v in ((o1, o2), (hT1, hT2), (chk1, chk2)):
+        assert relerr(v.cpu().numpy(), u.cpu().numpy()) <= 2e-5
+
+
 def test_no_gate():
     inp = scan_inputs(2, 50, 32, seed=3, random_A=True)
     res = _run(inp, gate=False)
