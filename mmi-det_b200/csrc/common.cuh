@@ -114,6 +114,23 @@ namespace mmi {
 int make_tmap_2d(CUtensorMap *map, const void *base, int dtype, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
                  uint32_t box_rows, uint32_t box_cols);
 
+int make_tmap_3d(CUtensorMap *map, const void *base, int dtype, uint64_t nb, uint64_t L, uint64_t cols, uint64_t pitch_bytes,
+                 uint32_t box_rows, uint32_t box_cols);
+
+// TMA engine, 3-D tile global -> shared; coordinates are {column, t, b} of a (B, L, cols) tensor.
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int col, int t, int b, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(col), "r"(t), "r"(b), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, int col, int t, int b, const void *src) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(col),
+                 "r"(t), "r"(b), "r"(smem_u32(src))
+                 : "memory");
+}
+
 // TMA engine, 2-D tile global -> shared (SASS: UTMALDG); coordinates are {column, row}.
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int col, int row, uint64_t *bar) {
     asm volatile(

@@ -65,16 +65,15 @@ int mmi_selscan_fwd_bwd_host(const void *x, const void *delta, const void *z, co
     const size_t big = al(size_t(B) * L * ED * es), bc = al(size_t(B) * L * N * es), an = al(size_t(ED) * N * 4), dn = al(size_t(ED) * 4);
     const int nchk = (L + kChunk - 1) / kChunk;
     const size_t chkb = al(size_t(B) * nchk * ED * N * 4), wsb = al(size_t(mmi_selscan_bwd_ws_bytes(B, L, ED, N)));
-    const size_t wsf = al(size_t(mmi_selscan_fwd_ws_bytes(B, L, ED, N)));
     // x delta z dout out dx ddelta dz | B C dB dC | A dA | D dD | chk | ws
-    const size_t total = 8 * big + 4 * bc + 2 * an + 2 * dn + chkb + wsb + wsf;
+    const size_t total = 8 * big + 4 * bc + 2 * an + 2 * dn + chkb + wsb;
     if (int e = hws_reserve(total)) return e;
     char *p = static_cast<char *>(g_hws.dev);
     auto take = [&](size_t n) { char *r = p; p += n; return r; };
     char *d_x = take(big), *d_d = take(big), *d_z = take(big), *d_g = take(big), *d_o = take(big), *d_dx = take(big),
          *d_dd = take(big), *d_dz = take(big);
     char *d_B = take(bc), *d_C = take(bc), *d_dB = take(bc), *d_dC = take(bc);
-    char *d_A = take(an), *d_dA = take(an), *d_D = take(dn), *d_dD = take(dn), *d_chk = take(chkb), *d_ws = take(wsb), *d_wsf = take(wsf);
+    char *d_A = take(an), *d_dA = take(an), *d_D = take(dn), *d_dD = take(dn), *d_chk = take(chkb), *d_ws = take(wsb);
     cudaStream_t st = g_hws.stream;
     const size_t nbig = size_t(B) * L * ED * es, nbc = size_t(B) * L * N * es;
 #define MMI_CP(dst, src, n, kind) \
@@ -88,7 +87,7 @@ int mmi_selscan_fwd_bwd_host(const void *x, const void *delta, const void *z, co
     MMI_CP(d_A, A, size_t(ED) * N * 4, cudaMemcpyHostToDevice);
     MMI_CP(d_D, D, size_t(ED) * 4, cudaMemcpyHostToDevice);
     if (int e = mmi_selscan_fwd(d_x, d_d, z ? d_z : nullptr, (const float *)d_A, d_B, d_C, (const float *)d_D, nullptr, d_o,
-                                nullptr, (float *)d_chk, d_wsf, B, L, ED, N, ED, ED, ED, ED, kChunk, dtype, flags, st))
+                                nullptr, (float *)d_chk, B, L, ED, N, ED, ED, ED, ED, kChunk, dtype, flags, st))
         return e;
     if (int e = mmi_selscan_bwd(d_x, d_d, z ? d_z : nullptr, (const float *)d_A, d_B, d_C, (const float *)d_D, d_g,
                                 (const float *)d_chk, d_dx, d_dd, z ? d_dz : nullptr, (float *)d_dA, d_dB, d_dC,

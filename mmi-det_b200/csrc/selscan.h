@@ -5,9 +5,7 @@
 
 namespace mmi {
 
-constexpr int kChunk = 16;    // state-checkpoint interval in timesteps (== backward tile length)
-constexpr int kFwdTile = 16;  // forward tile length, a multiple of kChunk
-constexpr int kMaxSeg = 64;   // upper bound on the number of L segments (sizes the workspaces)
+constexpr int kChunk = 16;  // state-checkpoint interval in timesteps == the chunk one warp scans per super-tile
 
 struct FwdParams {
     const void *x, *delta, *z, *Bm, *Cm;
@@ -17,10 +15,6 @@ struct FwdParams {
     int B, L, ED;
     int64_t x_ld, d_ld, z_ld, o_ld;
     int flags;
-    // L-split (filled by the launcher): segment s covers timesteps [s*seglen, (s+1)*seglen)
-    int nseg, seglen;
-    float *seg_state;  // (B, kMaxSeg, ED, N) local end state of each segment (scan started from zero)
-    float *seg_sumd;   // (B, kMaxSeg, ED)    sum of delta over the segment
 };
 
 struct BwdParams {
@@ -36,8 +30,7 @@ struct BwdParams {
     int flags;
 };
 
-int selscan_fwd_launch(const FwdParams &p, int dtype, void *ws, cudaStream_t st);
-int64_t selscan_fwd_ws_bytes(int B, int ED);
+int selscan_fwd_launch(const FwdParams &p, int dtype, cudaStream_t st);
 int selscan_bwd_launch(BwdParams p, int dtype, void *ws, cudaStream_t st);
 int64_t selscan_bwd_ws_bytes(int B, int L, int ED);
 int sm_count();

@@ -409,7 +409,10 @@ __global__ void selscan_bwd_finish_kernel(const float *__restrict__ ws_bc, const
     }
 }
 
-int pick_lpc(int B, int ED, int flags);
+static int pick_lpc(int B, int ED, int flags) {
+    (void)B; (void)flags;
+    return ED >= 64 ? 1 : ED >= 32 ? 2 : 4;
+}
 
 template <typename T, int LPC> static int launch_bwd_t(BwdParams p, int dtype, void *ws, cudaStream_t st) {
     constexpr int NW = 2, TC = kChunk, STAGES = 3;

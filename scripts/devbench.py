@@ -24,9 +24,8 @@ def main():
     ap.add_argument("--ED", type=int, default=512)
     ap.add_argument("--dtype", default="f32")
     ap.add_argument("--iters", type=int, default=10)
-    ap.add_argument("--lpcs", default="1,2,4")
+    ap.add_argument("--cfgs", default="0,1,2,3")
     ap.add_argument("--nobwd", action="store_true")
-    ap.add_argument("--nsegs", default="0")
     a = ap.parse_args()
     dt = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}[a.dtype]
     B, L, ED, N = a.B, a.L, a.ED, 16
@@ -60,12 +59,12 @@ def main():
         return ts[len(ts) // 2]
 
     for name, A in (("geomA", A_init), ("randA", A_rand)):
-      for nseg in [int(v) for v in a.nsegs.split(",")]:
-        for lpc in [int(v) for v in a.lpcs.split(",")]:
-            flags = (lpc << 4) | (nseg << 8)
+      for nseg in [0]:
+        for lpc in [int(v) for v in a.cfgs.split(",")]:
+            flags = lpc << 4
             t_inf = timeit(lambda: ops.selscan_fwd_raw(x, delta, A, Bm, Cm, D, z=z, flags=flags))
             t_f = timeit(lambda: ops.selscan_fwd_raw(x, delta, A, Bm, Cm, D, z=z, want_chk=True, flags=flags))
-            line = (f"{name} lpc={lpc} nseg={nseg}: fwd(no chk) {t_inf:.3f} ms {fb/t_inf/1e6:.0f} GB/s | fwd(+chk) {t_f:.3f} ms "
+            line = (f"{name} cfg={lpc}: fwd(no chk) {t_inf:.3f} ms {fb/t_inf/1e6:.0f} GB/s | fwd(+chk) {t_f:.3f} ms "
                     f"{fb/t_f/1e6:.0f} GB/s")
             if not a.nobwd:
                 _, _, chk, saved = ops.selscan_fwd_raw(x, delta, A, Bm, Cm, D, z=z, want_chk=True, flags=flags)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """One forward (+ optionally backward) launch of the fused scan for ncu captures.
-Usage: python scripts/prof_one.py [--B 16 --L 6400 --ED 512 --lpc 2 --bwd --randA --dtype f32]"""
+Usage: python scripts/prof_one.py [--B 16 --L 6400 --ED 512 --cfg 2 --bwd --randA --dtype f32]"""
 import argparse
 import os
 import sys
@@ -14,7 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--B", type=int, default=16)
 ap.add_argument("--L", type=int, default=6400)
 ap.add_argument("--ED", type=int, default=512)
-ap.add_argument("--lpc", type=int, default=0)
+ap.add_argument("--cfg", type=int, default=0)
 ap.add_argument("--bwd", action="store_true")
 ap.add_argument("--randA", action="store_true")
 ap.add_argument("--dtype", default="f32")
@@ -33,7 +33,7 @@ D = torch.ones(ED, device=dev)
 A = -torch.arange(1, N + 1, device=dev, dtype=torch.float32).repeat(ED, 1)
 if a.randA:
     A = -torch.exp(torch.randn(ED, N, device=dev) * 0.7 + 0.5)
-flags = a.lpc << 4
+flags = a.cfg << 4
 for _ in range(a.reps):
     out, _, chk, saved = ops.selscan_fwd_raw(x, delta, A, Bm, Cm, D, z=z, want_chk=True, flags=flags)
     if a.bwd:
