@@ -8,16 +8,26 @@
 //     dB[t,n] = sum_d g delta x;  dC[t,n] = sum_d dy h[t,n];  dA[d,n] = sum_{b,t} h[t-1] g a delta;  dD = sum dy x
 //     dz      = dout y sigma(z) (1 + z (1 - sigma(z)))
 // The reference keeps five padded (B,Lp,ED,N) tensors alive for this; here the forward pass leaves one state
-// checkpoint per kChunk steps and each chunk's states are recomputed into shared memory.
+// checkpoint per kChunk steps and each chunk's states are recomputed on chip.
 //
-// Per chunk (processed last to first), each warp runs four phases on its own 32/LPC channels:
-//   P1 (owner lanes, forward)  recompute h[t], park it in the shared history, compute dy
-//   P2 (transposed mapping)    dC[t,:] += sum over the warp's channels of dy * h[t]      (reads the history)
-//   P3 (owner lanes, reverse)  g recurrence, ddelta / dx / dz / dA / dD, overwrite history with g*delta*x
-//   P4 (transposed mapping)    dB[t,:] += sum over the warp's channels of the overwritten history
-// so the cross-channel reductions cost one conflict-free LDS.128 + FFMA2 pair per 4 states instead of a shuffle
-// butterfly.  Per-CTA dB/dC partials and per-batch dA/dD partials go to a workspace; selscan_bwd_finish_kernel
-// reduces them deterministically (no atomics).  Inputs arrive through the same TMA ring as the forward kernel.
+// Mapping.  A CTA owns 64 adjacent channels of one batch element and walks L backwards in super-tiles of
+// ST = WT*kChunk steps; warp wt owns chunk wt of the super-tile and each lane owns TWO adjacent channels with all
+// N = 16 states of both in registers (the B / C rows, which every lane needs, are then fetched once per two channels,
+// and the cross-channel sums for dB / dC start with an in-thread add).  Tiles of x / delta / dout / z / B / C arrive
+// through a TMA ring; dx / ddelta / dz are written in place over the x / delta / z tiles and leave through TMA stores.
+// Per super-tile, per warp:
+//   A   dy = dout*silu(z) and the dz factor e = dout*sigma(z)(1 + z(1-sigma(z))) (parked over the dout / z tiles), and the
+//       chunk's reverse-scan summary G[n] = sum_t exp(A[n]*(delta summed up to and including t)) dy[t] C[t,n] by direct
+//       evaluation -- the time axis is scanned by WT warps at once, exactly as in the forward kernel
+//   fold  after one CTA barrier each warp chains the summaries of the LATER chunks onto the carried a*g
+//   P1  forward recompute of h from the chunk's checkpoint; every state is parked in TENSOR MEMORY (tcgen05.st, one
+//       16-column slot per channel and step -- thread-private, so it costs no shared-memory bandwidth); y -> dz; the
+//       per-step products dy*h are pre-added over the lane's two channels and summed over the warp's 64 channels by
+//       a shared-memory transposition -> dC partial
+//   P3  reverse scan: h[t-1] comes back from tensor memory (tcgen05.ld), g recurrence, ddelta / dx / dA / dD, and the
+//       products g*delta*x are reduced the same way -> dB partial.
+// Per-CTA dB/dC partials and per-batch dA/dD partials go to a workspace; selscan_bwd_finish_kernel reduces them
+// deterministically (no atomics).
 #include <cstring>
 
 #include "../../include/mmidet_b200.h"
@@ -30,348 +40,509 @@ struct BwdMaps {
     CUtensorMap x, d, z, g, B, C, odx, odd, odz;
 };
 
-template <typename T, int LPC, int NW, int TC, int STAGES> struct BwdLayout {
-    static constexpr int N = kN, NS = N / LPC, K4 = NS / 4, CPW = 32 / LPC, CH = NW * CPW;
-    static constexpr size_t TILE_BYTES = size_t(TC) * CH * sizeof(T);
-    static constexpr size_t BCT_BYTES = size_t(TC) * N * sizeof(T);
-    static constexpr size_t CHK_BYTES = size_t(CH) * N * 4;
-    static constexpr size_t STAGE_BYTES = 4 * TILE_BYTES + 2 * BCT_BYTES + CHK_BYTES;
-    static constexpr size_t HIST_OFF = STAGES * STAGE_BYTES;
-    static constexpr size_t HIST_WARP_BYTES = size_t(TC + 1) * K4 * 512;
-    static constexpr size_t DYS_OFF = HIST_OFF + NW * HIST_WARP_BYTES;
-    static constexpr int DYS_LD = CPW + 1;
-    static constexpr size_t DBC_OFF = DYS_OFF + size_t(NW) * TC * DYS_LD * 4;
-    static constexpr size_t OUT_OFF = DBC_OFF + size_t(2) * NW * TC * N * 4;  // [2 buffers][dx, ddelta, dz] tiles
-    static constexpr size_t BC32_OFF = OUT_OFF + 6 * TILE_BYTES;
-    static constexpr size_t BAR_OFF = BC32_OFF + (sizeof(T) == 2 ? size_t(2) * TC * N * 4 : 0);
-    static constexpr size_t SMEM = BAR_OFF + STAGES * sizeof(uint64_t);
+constexpr int kRB = 4;  // steps per cross-channel reduction block
+
+template <typename T, int WT, int STAGES> struct BwdLayout {
+    static constexpr int N = kN, TC = kChunk, ST = WT * TC, CH = 64, NW = WT;
+    static constexpr size_t TILE_BYTES = size_t(ST) * CH * sizeof(T);
+    static constexpr size_t BCT_BYTES = size_t(ST) * N * sizeof(T);
+    static constexpr size_t STAGE_BYTES = 4 * TILE_BYTES + 2 * BCT_BYTES;  // x | delta | dout | z | B | C
+    static constexpr size_t DYE_OFF = STAGES * STAGE_BYTES;                // fp32 dy | e when T is 16 bit
+    static constexpr size_t DYE_BYTES = sizeof(T) == 2 ? size_t(2) * ST * CH * 4 : 0;
+    static constexpr size_t SCR_OFF = DYE_OFF + DYE_BYTES;                   // per warp [kRB][4][32] float4
+    static constexpr size_t SCR_WARP = size_t(kRB) * 4 * 32 * 16;
+    static constexpr size_t DA_OFF = SCR_OFF + NW * SCR_WARP;                // parked dA: [8][NW*32] float4
+    static constexpr size_t SUM_OFF = DA_OFF + size_t(8) * NW * 32 * 16;     // chunk summaries [WT][2][4][32] float4
+    static constexpr size_t SUMD_OFF = SUM_OFF + size_t(WT) * 2 * 4 * 32 * 16;  // chunk sum(delta) [WT][32] float2
+    static constexpr size_t CARRY_OFF = SUMD_OFF + size_t(WT) * 32 * 8;      // carried a*g [2][2][4][32] float4
+    static constexpr size_t BC32_OFF = CARRY_OFF + size_t(2) * 2 * 4 * 32 * 16;
+    static constexpr size_t BC32_BYTES = sizeof(T) == 2 ? size_t(NW) * 2 * TC * N * 4 : 0;
+    static constexpr size_t BAR_OFF = BC32_OFF + BC32_BYTES;
+    static constexpr size_t SMEM = BAR_OFF + STAGES * sizeof(uint64_t) + 16;
 };
 
-template <typename T, int LPC, int NW, int TC, int STAGES, bool GEOM, bool HAS_Z>
-__device__ __forceinline__ void bwd_body(const BwdParams &p, const BwdMaps &tm, unsigned char *smem,
-                                         const float (&A2)[kN / LPC], float A2base, float Dd, int c0, int chw, int b,
-                                         int cl, int c, bool active, int sub, int warp, int lane) {
-    using Lay = BwdLayout<T, LPC, NW, TC, STAGES>;
-    constexpr int N = kN, NS = Lay::NS, K4 = Lay::K4, CH = Lay::CH, NP = NS / 2;
-    constexpr float kLn2 = 0.6931471805599453f;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + Lay::BAR_OFF);
-    float4 *hist = reinterpret_cast<float4 *>(smem + Lay::HIST_OFF + warp * Lay::HIST_WARP_BYTES);  // [TC+1][K4][32]
-    float *dys = reinterpret_cast<float *>(smem + Lay::DYS_OFF) + warp * TC * Lay::DYS_LD;          // [TC][CPW+1]
-    float *dbc = reinterpret_cast<float *>(smem + Lay::DBC_OFF);                                    // [2][NW][TC][N]
-    float *bc32 = reinterpret_cast<float *>(smem + Lay::BC32_OFF);
+// ---- tensor memory as thread-private scratch: 16 fp32 per thread per op (lane = TMEM lane, 16 columns) -----------
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float2 (&v)[8]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "f"(v[0].x), "f"(v[0].y), "f"(v[1].x), "f"(v[1].y), "f"(v[2].x), "f"(v[2].y), "f"(v[3].x), "f"(v[3].y), "f"(v[4].x),
+        "f"(v[4].y), "f"(v[5].x), "f"(v[5].y), "f"(v[6].x), "f"(v[6].y), "f"(v[7].x), "f"(v[7].y)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float2 (&v)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x), "=f"(v[3].y),
+          "=f"(v[4].x), "=f"(v[4].y), "=f"(v[5].x), "=f"(v[5].y), "=f"(v[6].x), "=f"(v[6].y), "=f"(v[7].x), "=f"(v[7].y)
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-    const int L = p.L, ED = p.ED;
-    constexpr bool has_z = HAS_Z;
-    const int nch = (L + TC - 1) / TC;
-    const int64_t row_b = int64_t(b) * L;
-    const int chl = lane / LPC;  // channel within the warp
-    T *gdx = static_cast<T *>(p.dx), *gdd = static_cast<T *>(p.ddelta), *gdz = static_cast<T *>(p.dz);
-
-    auto stage_ptr = [&](int s) { return smem + size_t(s) * Lay::STAGE_BYTES; };
-    auto issue = [&](int s, int j) {  // elected thread: 6 TMA tiles + the chunk's state checkpoint
-        unsigned char *st = stage_ptr(s);
-        const int row0 = int(row_b) + j * TC;
-        const uint32_t total = uint32_t(Lay::TILE_BYTES) * (has_z ? 4u : 3u) + 2u * uint32_t(Lay::BCT_BYTES) +
-                               uint32_t(chw) * N * 4u;
-        mbar_arrive_expect_tx(&full[s], total);
-        tma_load_2d(st, &tm.x, c0, row0, &full[s]);
-        tma_load_2d(st + Lay::TILE_BYTES, &tm.d, c0, row0, &full[s]);
-        tma_load_2d(st + 2 * Lay::TILE_BYTES, &tm.g, c0, row0, &full[s]);
-        if (has_z) tma_load_2d(st + 3 * Lay::TILE_BYTES, &tm.z, c0, row0, &full[s]);
-        tma_load_2d(st + 4 * Lay::TILE_BYTES, &tm.B, 0, row0, &full[s]);
-        tma_load_2d(st + 4 * Lay::TILE_BYTES + Lay::BCT_BYTES, &tm.C, 0, row0, &full[s]);
-        bulk_g2s(st + 4 * Lay::TILE_BYTES + 2 * Lay::BCT_BYTES, p.chk + ((int64_t(b) * nch + j) * ED + c0) * N,
-                 uint32_t(chw) * N * 4u, &full[s]);
-    };
-
-    float2 A2p[NP], g2[NP], an2[NP], dA2[NP];
+template <bool GEOM> __device__ __forceinline__ void bdecay16(float dsum, float A2base, const float2 (&A2p)[8], float2 (&a2)[8]) {
+    if constexpr (GEOM) {
+        const float r = ex2(dsum * A2base), r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+        a2[0] = make_float2(r, r2);
+        a2[1] = mul2(a2[0], splat2(r2));
+        a2[2] = mul2(a2[0], splat2(r4));
+        a2[3] = mul2(a2[1], splat2(r4));
 #pragma unroll
-    for (int k = 0; k < NP; ++k) {
-        A2p[k] = make_float2(A2[2 * k], A2[2 * k + 1]);
-        g2[k] = an2[k] = dA2[k] = make_float2(0.f, 0.f);
-    }
-    float dDacc = 0.f;
-
-    auto decay = [&](float dv, float2(&a2)[NP]) {  // a[t,n] for this lane's states
-        if constexpr (GEOM) {
-            const float r = ex2(dv * A2base);
-            const float q = (LPC == 1) ? r : ex2(dv * A2[0]);
-            const float r2 = r * r;
-            a2[0] = make_float2(q, q * r);
-            if constexpr (NP >= 2) a2[1] = mul2(a2[0], splat2(r2));
-            if constexpr (NP >= 4) {
-                const float2 r4 = splat2(r2 * r2);
-                a2[2] = mul2(a2[0], r4);
-                a2[3] = mul2(a2[1], r4);
-            }
-            if constexpr (NP >= 8) {
-                const float r4s = r2 * r2;
-                const float2 r8 = splat2(r4s * r4s);
+        for (int k = 4; k < 8; ++k) a2[k] = mul2(a2[k - 4], splat2(r8));
+    } else {
+        const float2 d2 = splat2(dsum);
 #pragma unroll
-                for (int k = 4; k < 8; ++k) a2[k] = mul2(a2[k - 4], r8);
-            }
-        } else {
-            const float2 dv2 = splat2(dv);
-#pragma unroll
-            for (int k = 0; k < NP; ++k) {
-                const float2 e = mul2(dv2, A2p[k]);
-                a2[k] = make_float2(ex2(e.x), ex2(e.y));
-            }
+        for (int k = 0; k < 8; ++k) {
+            const float2 e = mul2(d2, A2p[k]);
+            a2[k] = make_float2(ex2(e.x), ex2(e.y));
         }
-    };
-
-    if (threadIdx.x == 0)
-        for (int s = 0; s < STAGES && s < nch; ++s) issue(s, nch - 1 - s);
-
-    for (int i = 0; i < nch; ++i) {
-        const int s = i % STAGES, j = nch - 1 - i;
-        const int t0 = j * TC, tl = min(TC, L - t0);
-        unsigned char *st = stage_ptr(s);
-        const T *sx = reinterpret_cast<const T *>(st), *sd = sx + TC * CH, *sg = sd + TC * CH, *sz = sg + TC * CH;
-        const T *sB = reinterpret_cast<const T *>(st + 4 * Lay::TILE_BYTES), *sC = sB + TC * N;
-        const float *sck = reinterpret_cast<const float *>(st + 4 * Lay::TILE_BYTES + 2 * Lay::BCT_BYTES);
-        mbar_wait(&full[s], (i / STAGES) & 1);
-
-        const float *fB, *fC;
-        if constexpr (sizeof(T) == 2) {
-            for (int q = threadIdx.x; q < 2 * TC * N; q += NW * 32) bc32[q] = to_f32<T>(sB[q]);
-            __syncthreads();
-            fB = bc32;
-            fC = bc32 + TC * N;
-        } else {
-            fB = reinterpret_cast<const float *>(sB);
-            fC = reinterpret_cast<const float *>(sC);
-        }
-        auto loadBC = [&](const float *base, int t, float2(&v)[NP]) {
-            const float4 *q = reinterpret_cast<const float4 *>(base + t * N + sub * NS);
-#pragma unroll
-            for (int k = 0; k < K4; ++k) {
-                const float4 w = q[k];
-                v[2 * k] = make_float2(w.x, w.y);
-                v[2 * k + 1] = make_float2(w.z, w.w);
-            }
-        };
-
-        // ---- P1: recompute the chunk's states from its checkpoint -----------------------------------------
-        float2 h2[NP];
-        {
-            const float4 *q = reinterpret_cast<const float4 *>(sck + cl * N + sub * NS);
-#pragma unroll
-            for (int k = 0; k < K4; ++k) {
-                const float4 w = active ? q[k] : make_float4(0.f, 0.f, 0.f, 0.f);
-                h2[2 * k] = make_float2(w.x, w.y);
-                h2[2 * k + 1] = make_float2(w.z, w.w);
-                hist[k * 32 + lane] = w;
-            }
-        }
-        auto p1_step = [&](int t) {
-            const float xv = to_f32<T>(sx[t * CH + cl]), dv = to_f32<T>(sd[t * CH + cl]);
-            float2 Bv[NP], a2[NP];
-            loadBC(fB, t, Bv);
-            decay(dv, a2);
-            const float2 dx2 = splat2(dv * xv);
-#pragma unroll
-            for (int k = 0; k < NP; ++k) h2[k] = fma2(a2[k], h2[k], mul2(dx2, Bv[k]));
-#pragma unroll
-            for (int k = 0; k < K4; ++k)
-                hist[((t + 1) * K4 + k) * 32 + lane] = make_float4(h2[2 * k].x, h2[2 * k].y, h2[2 * k + 1].x, h2[2 * k + 1].y);
-            float dy = to_f32<T>(sg[t * CH + cl]);
-            if constexpr (HAS_Z) {
-                const float zv = to_f32<T>(sz[t * CH + cl]);
-                dy *= zv * sigmoidf_fast(zv);
-            }
-            dys[t * Lay::DYS_LD + chl] = dy;  // the LPC lanes of a channel write the same value
-        };
-        if (tl == TC) {
-#pragma unroll
-            for (int t = 0; t < TC; ++t) p1_step(t);
-        } else {
-            for (int t = 0; t < tl; ++t) p1_step(t);
-        }
-        __syncwarp();
-
-        // ---- P2 / P4: sum the history over this warp's channels (lane l walks entries (i + l) & 31) ---------
-        auto reduce_hist = [&](float *dst, bool weighted) {
-#pragma unroll
-            for (int jj = 0; jj < (TC * K4 + 31) / 32; ++jj) {
-                const int id = lane + 32 * jj;
-                const int t = id / K4, k = id % K4;
-                if (id < TC * K4 && t < tl) {
-                    float2 acc[LPC][2];
-#pragma unroll
-                    for (int q = 0; q < LPC; ++q) acc[q][0] = acc[q][1] = make_float2(0.f, 0.f);
-                    const float4 *src = hist + ((t + 1) * K4 + k) * 32;
-                    const float *dyr = dys + t * Lay::DYS_LD;
-#pragma unroll 4
-                    for (int i0 = 0; i0 < 32; i0 += LPC) {
-#pragma unroll
-                        for (int q = 0; q < LPC; ++q) {
-                            const int e = (i0 + q + lane) & 31;
-                            const float4 v = src[e];
-                            const float2 m = splat2(weighted ? dyr[e / LPC] : 1.0f);
-                            acc[q][0] = fma2(m, make_float2(v.x, v.y), acc[q][0]);
-                            acc[q][1] = fma2(m, make_float2(v.z, v.w), acc[q][1]);
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < LPC; ++q) {
-                        const int se = (q + lane) % LPC;  // which state slice entry e belonged to
-                        *reinterpret_cast<float4 *>(dst + t * N + se * NS + 4 * k) =
-                            make_float4(acc[q][0].x, acc[q][0].y, acc[q][1].x, acc[q][1].y);
-                    }
-                }
-            }
-        };
-        reduce_hist(dbc + (NW + warp) * TC * N, true);  // dC partial of this warp
-        __syncwarp();
-
-        // ---- P3: reverse scan -----------------------------------------------------------------------------
-        float2 hc2[NP];
-#pragma unroll
-        for (int k = 0; k < NP; ++k) hc2[k] = h2[k];
-        T *so = reinterpret_cast<T *>(smem + Lay::OUT_OFF + (i & 1) * 3 * Lay::TILE_BYTES) + cl;  // dx | ddelta | dz tiles
-        auto p3_step = [&](int t, bool to_smem) {
-            const float xv = to_f32<T>(sx[t * CH + cl]), dv = to_f32<T>(sd[t * CH + cl]);
-            const float gv = to_f32<T>(sg[t * CH + cl]);
-            float2 Bv[NP], Cv[NP], a2[NP], hp2[NP];
-            loadBC(fB, t, Bv);
-            loadBC(fC, t, Cv);
-            decay(dv, a2);
-#pragma unroll
-            for (int k = 0; k < K4; ++k) {
-                const float4 w = hist[(t * K4 + k) * 32 + lane];
-                hp2[2 * k] = make_float2(w.x, w.y);
-                hp2[2 * k + 1] = make_float2(w.z, w.w);
-            }
-            float zv = 0.f, sig = 1.f, dy = gv;
-            if constexpr (HAS_Z) {
-                zv = to_f32<T>(sz[t * CH + cl]);
-                sig = sigmoidf_fast(zv);
-                dy = gv * zv * sig;
-            }
-            const float2 dy2 = splat2(dy), dv2 = splat2(dv), dx2 = splat2(dv * xv);
-            float2 ya = make_float2(0.f, 0.f), dda = make_float2(0.f, 0.f), gBa = make_float2(0.f, 0.f);
-            float2 gd[NP];
-#pragma unroll
-            for (int k = 0; k < NP; ++k) {
-                ya = fma2(Cv[k], hc2[k], ya);                         // y[t] readout (for dz)
-                g2[k] = fma2(an2[k], g2[k], mul2(dy2, Cv[k]));        // g[t]
-                const float2 tmp = mul2(mul2(hp2[k], g2[k]), a2[k]);  // h[t-1] g a
-                dda = fma2(tmp, A2p[k], dda);
-                dA2[k] = fma2(tmp, dv2, dA2[k]);
-                gBa = fma2(g2[k], Bv[k], gBa);
-                gd[k] = mul2(g2[k], dx2);
-                an2[k] = a2[k];
-                hc2[k] = hp2[k];
-            }
-#pragma unroll
-            for (int k = 0; k < K4; ++k)
-                hist[((t + 1) * K4 + k) * 32 + lane] = make_float4(gd[2 * k].x, gd[2 * k].y, gd[2 * k + 1].x, gd[2 * k + 1].y);
-            float y = ya.x + ya.y, dd = (dda.x + dda.y) * kLn2, gB = gBa.x + gBa.y;
-            if constexpr (LPC >= 2) {
-                y += __shfl_xor_sync(0xffffffffu, y, 1);
-                dd += __shfl_xor_sync(0xffffffffu, dd, 1);
-                gB += __shfl_xor_sync(0xffffffffu, gB, 1);
-            }
-            if constexpr (LPC >= 4) {
-                y += __shfl_xor_sync(0xffffffffu, y, 2);
-                dd += __shfl_xor_sync(0xffffffffu, dd, 2);
-                gB += __shfl_xor_sync(0xffffffffu, gB, 2);
-            }
-            y = fmaf(Dd, xv, y);
-            dDacc = fmaf(dy, xv, dDacc);
-            const T odx = from_f32<T>(fmaf(gB, dv, Dd * dy)), odd = from_f32<T>(fmaf(gB, xv, dd));
-            const T odz = from_f32<T>(gv * y * sig * fmaf(zv, 1.f - sig, 1.f));
-            if (to_smem) {  // the LPC lanes of a channel write identical values
-                so[t * CH] = odx;
-                so[TC * CH + t * CH] = odd;
-                if constexpr (HAS_Z) so[2 * TC * CH + t * CH] = odz;
-            } else if (active && sub == 0) {
-                const int64_t o = (row_b + t0 + t) * ED + c;
-                gdx[o] = odx;
-                gdd[o] = odd;
-                if constexpr (HAS_Z) gdz[o] = odz;
-            }
-        };
-        if (tl == TC) {
-#pragma unroll
-            for (int t = TC - 1; t >= 0; --t) p3_step(t, true);
-            fence_proxy_async();
-        } else {
-            for (int t = tl - 1; t >= 0; --t) p3_step(t, false);
-        }
-        __syncwarp();
-        reduce_hist(dbc + warp * TC * N, false);  // dB partial of this warp
-        if (threadIdx.x == 0) bulk_wait_read<0>();  // the previous chunk's tile stores have drained their buffers
-        __syncthreads();
-
-        // ---- combine the warps' partials, one 128-byte row [dB(16) | dC(16)] per timestep --------------------
-        for (int q = threadIdx.x; q < tl * 2 * N; q += NW * 32) {
-            const int t = q / (2 * N), r = q % (2 * N), which = r / N, n = r % N;
-            float v = 0.f;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) v += dbc[((which * NW + w) * TC + t) * N + n];
-            p.ws_bc[((row_b + t0 + t) * p.ntile_c + blockIdx.x) * (2 * N) + r] = v;
-        }
-        __syncthreads();  // stage s, history and dbc are free again
-        if (threadIdx.x == 0) {
-            if (tl == TC) {
-                const T *ob = so - cl;
-                tma_store_2d(&tm.odx, c0, int(row_b) + t0, ob);
-                tma_store_2d(&tm.odd, c0, int(row_b) + t0, ob + TC * CH);
-                if (HAS_Z) tma_store_2d(&tm.odz, c0, int(row_b) + t0, ob + 2 * TC * CH);
-                bulk_commit();
-            }
-            if (i + STAGES < nch) issue(s, nch - 1 - (i + STAGES));
-        }
-    }
-    if (threadIdx.x == 0) bulk_wait_read<0>();
-
-    if (active) {  // per-batch partials of dA (pre-scaled A2 -> A handled above), dD
-        float *o = p.ws_ad + (int64_t(b) * ED + c) * (N + 1);
-#pragma unroll
-        for (int k = 0; k < NP; ++k) {
-            o[sub * NS + 2 * k] = dA2[k].x;
-            o[sub * NS + 2 * k + 1] = dA2[k].y;
-        }
-        if (sub == 0) o[N] = dDacc;
     }
 }
 
-template <typename T, int LPC, int NW, int TC, int STAGES>
-__global__ void __launch_bounds__(NW * 32) selscan_bwd_kernel(const BwdParams p, const __grid_constant__ BwdMaps tm) {
-    using Lay = BwdLayout<T, LPC, NW, TC, STAGES>;
-    constexpr int N = kN, NS = Lay::NS, CPW = Lay::CPW, CH = Lay::CH;
+__device__ __forceinline__ void bload16(const float *p, float2 (&v)[8]) {
+    const float4 *q = reinterpret_cast<const float4 *>(p);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float4 w = q[k];
+        v[2 * k] = make_float2(w.x, w.y);
+        v[2 * k + 1] = make_float2(w.z, w.w);
+    }
+}
+
+// two adjacent elements of a tile row (the lane's two channels)
+template <typename T> __device__ __forceinline__ float2 ld_pair(const T *p);
+template <> __device__ __forceinline__ float2 ld_pair<float>(const float *p) { return *reinterpret_cast<const float2 *>(p); }
+template <> __device__ __forceinline__ float2 ld_pair<__nv_bfloat16>(const __nv_bfloat16 *p) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(p));
+}
+template <> __device__ __forceinline__ float2 ld_pair<__half>(const __half *p) {
+    return __half22float2(*reinterpret_cast<const __half2 *>(p));
+}
+template <typename T> __device__ __forceinline__ void st_pair(T *p, float2 v);
+template <> __device__ __forceinline__ void st_pair<float>(float *p, float2 v) { *reinterpret_cast<float2 *>(p) = v; }
+template <> __device__ __forceinline__ void st_pair<__nv_bfloat16>(__nv_bfloat16 *p, float2 v) {
+    *reinterpret_cast<__nv_bfloat162 *>(p) = __float22bfloat162_rn(v);
+}
+template <> __device__ __forceinline__ void st_pair<__half>(__half *p, float2 v) {
+    *reinterpret_cast<__half2 *>(p) = __float22half2_rn(v);
+}
+__device__ __forceinline__ float pick(float2 v, int j) { return j ? v.y : v.x; }
+
+template <typename T, int WT, int STAGES, bool GEOM, bool HAS_Z>
+__device__ __forceinline__ void bwd_body(const BwdParams &p, const BwdMaps &tm, unsigned char *smem, uint32_t tmem_base,
+                                         const float2 (&A2p)[2][8], const float (&A2base)[2], const float (&Dd)[2], int c0,
+                                         int b, int wt, int lane, int c, const bool (&active)[2]) {
+    using Lay = BwdLayout<T, WT, STAGES>;
+    constexpr int N = kN, TC = Lay::TC, ST = Lay::ST, CH = Lay::CH, NW = Lay::NW;
+    constexpr float kLn2 = 0.6931471805599453f;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + Lay::BAR_OFF);
+    float4 *scr = reinterpret_cast<float4 *>(smem + Lay::SCR_OFF + wt * Lay::SCR_WARP);           // [kRB][4][32]
+    float4 *dApark = reinterpret_cast<float4 *>(smem + Lay::DA_OFF) + wt * 32 + lane;             // + k * NW*32
+    float4 *sumG = reinterpret_cast<float4 *>(smem + Lay::SUM_OFF);                                // [WT][2][4][32]
+    float2 *sumD = reinterpret_cast<float2 *>(smem + Lay::SUMD_OFF);                               // [WT][32]
+    float4 *carry = reinterpret_cast<float4 *>(smem + Lay::CARRY_OFF) + lane;                      // [2][2][4][32]
+    float *bc32 = reinterpret_cast<float *>(smem + Lay::BC32_OFF) + wt * 2 * TC * N;
+    const uint32_t tslot = tmem_base + (uint32_t(wt & 3) * 32u << 16) + uint32_t(wt >> 2) * (2 * TC * N);
+
+    const int L = p.L, ED = p.ED;
+    const int ntiles = (L + ST - 1) / ST, nchk = (L + TC - 1) / TC;
+    const int tb = wt * TC, cl = 2 * lane;
+    const int64_t row_b = int64_t(b) * L;
+
+    auto issue = [&](int s, int tj) {  // one elected thread: the 6 tile loads of super-tile tj arrive on full[s]
+        unsigned char *st = smem + size_t(s) * Lay::STAGE_BYTES;
+        const uint32_t total = uint32_t(Lay::TILE_BYTES) * (HAS_Z ? 4u : 3u) + 2u * uint32_t(Lay::BCT_BYTES);
+        mbar_arrive_expect_tx(&full[s], total);
+        tma_load_3d(st, &tm.x, c0, tj * ST, b, &full[s]);
+        tma_load_3d(st + Lay::TILE_BYTES, &tm.d, c0, tj * ST, b, &full[s]);
+        tma_load_3d(st + 2 * Lay::TILE_BYTES, &tm.g, c0, tj * ST, b, &full[s]);
+        if (HAS_Z) tma_load_3d(st + 3 * Lay::TILE_BYTES, &tm.z, c0, tj * ST, b, &full[s]);
+        tma_load_3d(st + 4 * Lay::TILE_BYTES, &tm.B, 0, tj * ST, b, &full[s]);
+        tma_load_3d(st + 4 * Lay::TILE_BYTES + Lay::BCT_BYTES, &tm.C, 0, tj * ST, b, &full[s]);
+    };
+
+    // zero the carried a*g (buffer 0) and the parked dA
+    if (wt == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) carry[k * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dApark[k * NW * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float dDacc[2] = {0.f, 0.f};
+    if (threadIdx.x == 0)
+        for (int s = 0; s < STAGES && s < ntiles; ++s) issue(s, ntiles - 1 - s);
+
+    // sum over the warp's 64 channels of the per-lane vectors parked in `scr` ([kRB][4][32] float4, one float4 per
+    // (step, state quad, lane)); lane l sums 16 source lanes of item l & 15, halves combined by one shuffle.
+    // which = 0: dB, 1: dC.  Partials go to ws_bc[(row * ntile_c + blockIdx.x) * 32 + which * 16 + n].
+    auto reduce_block = [&](int tblk, int which) {
+        __syncwarp();
+        const int item = lane & 15, half = lane >> 4;
+        const float4 *src = scr + item * 32 + half * 16;
+        float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float4 v = src[(i + lane) & 15];
+            s0 = add2(s0, make_float2(v.x, v.y));
+            s1 = add2(s1, make_float2(v.z, v.w));
+        }
+        s0.x += __shfl_xor_sync(0xffffffffu, s0.x, 16);
+        s0.y += __shfl_xor_sync(0xffffffffu, s0.y, 16);
+        s1.x += __shfl_xor_sync(0xffffffffu, s1.x, 16);
+        s1.y += __shfl_xor_sync(0xffffffffu, s1.y, 16);
+        const int t = tblk + (item >> 2), k4 = item & 3;
+        if (half == 0 && t < L)
+            __stcs(reinterpret_cast<float4 *>(p.ws_bc + ((row_b + t) * p.ntile_c + blockIdx.x) * (2 * N) + which * N + 4 * k4),
+                   make_float4(s0.x, s0.y, s1.x, s1.y));
+        __syncwarp();
+    };
+
+    for (int it = 0; it < ntiles; ++it) {
+        const int s = it % STAGES, tj = ntiles - 1 - it, t0 = tj * ST;
+        unsigned char *st = smem + size_t(s) * Lay::STAGE_BYTES;
+        T *sx = reinterpret_cast<T *>(st) + tb * CH + cl, *sd = sx + ST * CH, *sg = sd + ST * CH, *sz = sg + ST * CH;
+        float *sdy, *se;  // fp32 dy and dz factor: in place over dout / z for fp32 I/O, separate arrays for 16-bit I/O
+        if constexpr (sizeof(T) == 2) {
+            sdy = reinterpret_cast<float *>(smem + Lay::DYE_OFF) + tb * CH + cl;
+            se = sdy + ST * CH;
+        } else {
+            sdy = reinterpret_cast<float *>(sg);
+            se = reinterpret_cast<float *>(sz);
+        }
+        mbar_wait(&full[s], (it / STAGES) & 1);
+
+        const float *fB, *fC;
+        if constexpr (sizeof(T) == 2) {
+            const T *gB = reinterpret_cast<const T *>(st + 4 * Lay::TILE_BYTES) + tb * N;
+            const T *gC = reinterpret_cast<const T *>(st + 4 * Lay::TILE_BYTES + Lay::BCT_BYTES) + tb * N;
+            for (int i = lane; i < TC * N; i += 32) {
+                bc32[i] = to_f32<T>(gB[i]);
+                bc32[TC * N + i] = to_f32<T>(gC[i]);
+            }
+            __syncwarp();
+            fB = bc32;
+            fC = bc32 + TC * N;
+        } else {
+            fB = reinterpret_cast<const float *>(st + 4 * Lay::TILE_BYTES) + tb * N;
+            fC = reinterpret_cast<const float *>(st + 4 * Lay::TILE_BYTES + Lay::BCT_BYTES) + tb * N;
+        }
+
+        // chunk checkpoint (state entering step t0 + tb): issued now, consumed in P1
+        float4 ckv[2][4];
+        {
+            const bool inb = t0 + tb < L;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float4 *ck = reinterpret_cast<const float4 *>(
+                    p.chk + ((int64_t(b) * nchk + (inb ? (t0 + tb) / TC : 0)) * ED + (active[j] ? c + j : 0)) * N);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ckv[j][k] = (inb && active[j]) ? __ldcs(ck + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+
+        // ---- A: dy, dz factor, reverse-scan summary of the chunk ------------------------------------------------
+        float2 acc[2][8];
+        float S[2] = {0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[j][k] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < TC; ++u) {
+            const float2 dv = ld_pair<T>(sd + u * CH), gv = ld_pair<T>(sg + u * CH);
+            float2 dy = gv, ee = make_float2(0.f, 0.f);
+            if constexpr (HAS_Z) {
+                const float2 zv = ld_pair<T>(sz + u * CH);
+                const float sx_ = sigmoidf_fast(zv.x), sy_ = sigmoidf_fast(zv.y);
+                const float gsx = gv.x * sx_, gsy = gv.y * sy_;
+                dy = make_float2(gsx * zv.x, gsy * zv.y);
+                ee = make_float2(gsx * fmaf(zv.x, 1.f - sx_, 1.f), gsy * fmaf(zv.y, 1.f - sy_, 1.f));
+                *reinterpret_cast<float2 *>(se + u * CH) = ee;
+            }
+            if constexpr (HAS_Z || sizeof(T) == 2) *reinterpret_cast<float2 *>(sdy + u * CH) = dy;
+            float2 Cv[8];
+            bload16(fC + u * N, Cv);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                S[j] += pick(dv, j);
+                float2 pw[8];
+                const float dyj = pick(dy, j);
+                if constexpr (GEOM) {
+                    const float r = ex2(S[j] * A2base[j]), r2 = r * r, r4 = r2 * r2, r8 = r4 * r4, p0 = dyj * r;
+                    pw[0] = make_float2(p0, p0 * r);
+                    pw[1] = mul2(pw[0], splat2(r2));
+                    pw[2] = mul2(pw[0], splat2(r4));
+                    pw[3] = mul2(pw[1], splat2(r4));
+#pragma unroll
+                    for (int k = 4; k < 8; ++k) pw[k] = mul2(pw[k - 4], splat2(r8));
+                } else {
+                    const float2 S2 = splat2(S[j]), dy2 = splat2(dyj);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float2 e = mul2(S2, A2p[j][k]);
+                        pw[k] = mul2(dy2, make_float2(ex2(e.x), ex2(e.y)));
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[j][k] = fma2(pw[k], Cv[k], acc[j][k]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                sumG[((wt * 2 + j) * 4 + k) * 32 + lane] =
+                    make_float4(acc[j][2 * k].x, acc[j][2 * k].y, acc[j][2 * k + 1].x, acc[j][2 * k + 1].y);
+        sumD[wt * 32 + lane] = make_float2(S[0], S[1]);
+        __syncthreads();  // summaries of this super-tile (and the carry written during the previous one) are visible
+
+        // the previous super-tile's output stores have had a whole sweep to drain; its stage can be refilled
+        if (threadIdx.x == 0 && it >= 1 && it - 1 + STAGES < ntiles) {
+            bulk_wait_read<0>();
+            issue((it - 1) % STAGES, ntiles - 1 - (it - 1 + STAGES));
+        }
+
+        // ---- fold: a*g entering this chunk from the later ones --------------------------------------------------
+        float2 ga[2][8];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float4 *cin = carry + ((it & 1) * 2 + j) * 4 * 32;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float4 w = cin[k * 32];
+                ga[j][2 * k] = make_float2(w.x, w.y);
+                ga[j][2 * k + 1] = make_float2(w.z, w.w);
+            }
+        }
+#pragma unroll
+        for (int v = WT - 1; v >= 1; --v) {
+            if (v > wt) {
+                const float2 sdv = sumD[v * 32 + lane];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    float2 a2[8];
+                    bdecay16<GEOM>(pick(sdv, j), A2base[j], A2p[j], a2);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float4 w = sumG[((v * 2 + j) * 4 + k) * 32 + lane];
+                        ga[j][2 * k] = fma2(a2[2 * k], ga[j][2 * k], make_float2(w.x, w.y));
+                        ga[j][2 * k + 1] = fma2(a2[2 * k + 1], ga[j][2 * k + 1], make_float2(w.z, w.w));
+                    }
+                }
+            }
+        }
+        if (wt == 0) {  // carry for the next (earlier) super-tile = this chunk's entry value pushed through its summary
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                float2 a2[8];
+                bdecay16<GEOM>(S[j], A2base[j], A2p[j], a2);
+                float4 *cout = carry + (((it + 1) & 1) * 2 + j) * 4 * 32;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 v0 = fma2(a2[2 * k], ga[j][2 * k], acc[j][2 * k]);
+                    const float2 v1 = fma2(a2[2 * k + 1], ga[j][2 * k + 1], acc[j][2 * k + 1]);
+                    cout[k * 32] = make_float4(v0.x, v0.y, v1.x, v1.y);
+                }
+            }
+        }
+
+        // ---- P1: recompute the chunk's states; park them in tensor memory; y -> dz; dC -------------------------
+        float2 h[2][8];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                h[j][2 * k] = make_float2(ckv[j][k].x, ckv[j][k].y);
+                h[j][2 * k + 1] = make_float2(ckv[j][k].z, ckv[j][k].w);
+            }
+#pragma unroll 1
+        for (int ub = 0; ub < TC; ub += kRB) {
+#pragma unroll
+            for (int uu = 0; uu < kRB; ++uu) {
+                const int u = ub + uu;
+                const float2 xv = ld_pair<T>(sx + u * CH), dv = ld_pair<T>(sd + u * CH);
+                const float2 dy = *reinterpret_cast<const float2 *>(sdy + u * CH);
+                float2 Bv[8], Cv[8], pc[8];
+                bload16(fB + u * N, Bv);
+                bload16(fC + u * N, Cv);
+                float yy[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    tmem_st16(tslot + uint32_t((u * 2 + j) * N), h[j]);  // slot u = state ENTERING step u
+                    float2 a2[8];
+                    bdecay16<GEOM>(pick(dv, j), A2base[j], A2p[j], a2);
+                    const float2 dx2 = splat2(pick(dv, j) * pick(xv, j)), dy2 = splat2(pick(dy, j));
+                    float2 ya = make_float2(0.f, 0.f), yb = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        h[j][k] = fma2(a2[k], h[j][k], mul2(dx2, Bv[k]));
+                        if (k & 1) yb = fma2(Cv[k], h[j][k], yb);
+                        else ya = fma2(Cv[k], h[j][k], ya);
+                        pc[k] = j ? fma2(dy2, h[j][k], pc[k]) : mul2(dy2, h[j][k]);
+                    }
+                    ya = add2(ya, yb);
+                    yy[j] = fmaf(Dd[j], pick(xv, j), ya.x + ya.y);
+                }
+                if constexpr (HAS_Z) {
+                    const float2 ee = *reinterpret_cast<const float2 *>(se + u * CH);
+                    st_pair<T>(sz + u * CH, make_float2(yy[0] * ee.x, yy[1] * ee.y));  // dz, in place over z
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    scr[(uu * 4 + k) * 32 + lane] = make_float4(pc[2 * k].x, pc[2 * k].y, pc[2 * k + 1].x, pc[2 * k + 1].y);
+            }
+            reduce_block(t0 + tb + ub, 1);
+        }
+        tmem_wait_st();
+
+        // ---- P3: reverse scan ---------------------------------------------------------------------------------
+        float2 dA2[2][8];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float4 w = dApark[(j * 4 + k) * NW * 32];
+                dA2[j][2 * k] = make_float2(w.x, w.y);
+                dA2[j][2 * k + 1] = make_float2(w.z, w.w);
+            }
+#pragma unroll 1
+        for (int ub = TC - kRB; ub >= 0; ub -= kRB) {
+#pragma unroll
+            for (int uu = kRB - 1; uu >= 0; --uu) {
+                const int u = ub + uu;
+                float2 hp[2][8];
+                tmem_ld16(tslot + uint32_t((u * 2) * N), hp[0]);
+                tmem_ld16(tslot + uint32_t((u * 2 + 1) * N), hp[1]);
+                const float2 xv = ld_pair<T>(sx + u * CH), dv = ld_pair<T>(sd + u * CH);
+                const float2 dy = *reinterpret_cast<const float2 *>(sdy + u * CH);
+                float2 Bv[8], Cv[8], pb[8];
+                bload16(fB + u * N, Bv);
+                bload16(fC + u * N, Cv);
+                tmem_wait_ld();
+                float odx[2], odd[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    float2 a2[8];
+                    const float dvj = pick(dv, j), xvj = pick(xv, j), dyj = pick(dy, j);
+                    bdecay16<GEOM>(dvj, A2base[j], A2p[j], a2);
+                    const float2 dy2 = splat2(dyj), dv2 = splat2(dvj), dxw = splat2(dvj * xvj);
+                    float2 dda = make_float2(0.f, 0.f), ddb = make_float2(0.f, 0.f);
+                    float2 gBa = make_float2(0.f, 0.f), gBb = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float2 g = fma2(Cv[k], dy2, ga[j][k]);  // g[t] = C dy + a[t+1] g[t+1]
+                        const float2 ag = mul2(a2[k], g);             // a[t] g[t]   (carried to step t-1)
+                        const float2 w = mul2(hp[j][k], ag);          // h[t-1] a g
+                        float2 Aw;
+                        if constexpr (GEOM) Aw = make_float2(float(2 * k + 1), float(2 * k + 2));
+                        else Aw = A2p[j][k];
+                        if (k & 1) {
+                            ddb = fma2(w, Aw, ddb);
+                            gBb = fma2(g, Bv[k], gBb);
+                        } else {
+                            dda = fma2(w, Aw, dda);
+                            gBa = fma2(g, Bv[k], gBa);
+                        }
+                        dA2[j][k] = fma2(w, dv2, dA2[j][k]);
+                        pb[k] = j ? fma2(dxw, g, pb[k]) : mul2(dxw, g);
+                        ga[j][k] = ag;
+                    }
+                    dda = add2(dda, ddb);
+                    gBa = add2(gBa, gBb);
+                    float dd = (dda.x + dda.y) * kLn2;
+                    if constexpr (GEOM) dd *= A2base[j];
+                    const float gB = gBa.x + gBa.y;
+                    odx[j] = fmaf(gB, dvj, Dd[j] * dyj);
+                    odd[j] = fmaf(gB, xvj, dd);
+                    dDacc[j] = fmaf(dyj, xvj, dDacc[j]);
+                }
+                st_pair<T>(sx + u * CH, make_float2(odx[0], odx[1]));  // dx, in place over x
+                st_pair<T>(sd + u * CH, make_float2(odd[0], odd[1]));  // ddelta, in place over delta
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    scr[(uu * 4 + k) * 32 + lane] = make_float4(pb[2 * k].x, pb[2 * k].y, pb[2 * k + 1].x, pb[2 * k + 1].y);
+            }
+            reduce_block(t0 + tb + ub, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                dApark[(j * 4 + k) * NW * 32] = make_float4(dA2[j][2 * k].x, dA2[j][2 * k].y, dA2[j][2 * k + 1].x, dA2[j][2 * k + 1].y);
+
+        fence_proxy_async();  // generic-proxy writes of the in-place output tiles -> visible to the TMA engine
+        __syncthreads();      // every warp is done with stage s
+        if (threadIdx.x == 0) {
+            tma_store_3d(&tm.odx, c0, t0, b, st);
+            tma_store_3d(&tm.odd, c0, t0, b, st + Lay::TILE_BYTES);
+            if (HAS_Z) tma_store_3d(&tm.odz, c0, t0, b, st + 3 * Lay::TILE_BYTES);
+            bulk_commit();
+        }
+    }
+    if (threadIdx.x == 0) bulk_wait_read<0>();
+    __syncthreads();
+
+    // per-(batch, time-warp) partials of dA (A2 is A*log2e: dA = sum w delta, no rescale needed) and dD
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        if (active[j]) {
+            float *o = p.ws_ad + ((int64_t(b) * NW + wt) * ED + c + j) * (N + 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float4 w = dApark[(j * 4 + k) * NW * 32];
+                o[4 * k] = w.x;
+                o[4 * k + 1] = w.y;
+                o[4 * k + 2] = w.z;
+                o[4 * k + 3] = w.w;
+            }
+            o[N] = dDacc[j];
+        }
+    }
+}
+
+template <typename T, int WT, int STAGES>
+__global__ void __launch_bounds__(WT * 32, 1) selscan_bwd_kernel(const BwdParams p, const __grid_constant__ BwdMaps tm) {
+    using Lay = BwdLayout<T, WT, STAGES>;
+    constexpr int N = kN, CH = Lay::CH;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + Lay::BAR_OFF);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Lay::BAR_OFF + STAGES * sizeof(uint64_t));
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, wt = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y, c0 = blockIdx.x * CH;
-    const int chw = min(CH, p.ED - c0);
-    const int sub = lane % LPC;
-    const int cl = warp * CPW + lane / LPC;
-    const int c = c0 + cl;
-    const bool active = c < p.ED;
+    const int c = c0 + 2 * lane;
+    const bool active[2] = {c < p.ED, c + 1 < p.ED};
 
+    if (wt == 0) {  // all 512 tensor-memory columns: the state history of this CTA's 64 channels x WT chunks
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
         fence_mbar_init();
     }
-    const int cc = active ? c : p.ED - 1;
-    float A2[NS];
-    const float A2base = p.A[int64_t(cc) * N] * kLog2e;
+
+    float2 A2p[2][8];
+    float A2base[2], Dd[2];
     bool ok = !(p.flags & MMI_FLAG_NO_GEOM);
 #pragma unroll
-    for (int k = 0; k < NS; ++k) {
-        A2[k] = p.A[int64_t(cc) * N + sub * NS + k] * kLog2e;
-        const float want = float(sub * NS + k + 1) * A2base;
-        ok = ok && (fabsf(A2[k] - want) <= 2e-6f * fabsf(want));
+    for (int j = 0; j < 2; ++j) {
+        const int cc = active[j] ? c + j : p.ED - 1;
+        A2base[j] = p.A[int64_t(cc) * N] * kLog2e;
+        Dd[j] = p.D[cc];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            A2p[j][k] = make_float2(p.A[int64_t(cc) * N + 2 * k] * kLog2e, p.A[int64_t(cc) * N + 2 * k + 1] * kLog2e);
+            const float w0 = float(2 * k + 1) * A2base[j], w1 = float(2 * k + 2) * A2base[j];
+            ok = ok && (fabsf(A2p[j][k].x - w0) <= 2e-6f * fabsf(w0)) && (fabsf(A2p[j][k].y - w1) <= 2e-6f * fabsf(w1));
+        }
     }
-    const float Dd = p.D[cc];
-    const bool geom = __syncthreads_and(ok);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    const bool geom = __syncthreads_and(ok);  // also publishes the mbarrier inits and the tensor-memory base address
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
     const bool has_z = p.z != nullptr;
-#define MMI_BWD_BODY(G, Z) \
-    bwd_body<T, LPC, NW, TC, STAGES, G, Z>(p, tm, smem, A2, A2base, Dd, c0, chw, b, cl, c, active, sub, warp, lane)
+#define MMI_BWD_BODY(G, Z) bwd_body<T, WT, STAGES, G, Z>(p, tm, smem, tmem_base, A2p, A2base, Dd, c0, b, wt, lane, c, active)
     if (geom) {
         if (has_z) MMI_BWD_BODY(true, true);
         else MMI_BWD_BODY(true, false);
@@ -380,12 +551,15 @@ __global__ void __launch_bounds__(NW * 32) selscan_bwd_kernel(const BwdParams p,
         else MMI_BWD_BODY(false, false);
     }
 #undef MMI_BWD_BODY
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (wt == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
-// Deterministic reduction of the workspace partials: dB/dC over channel tiles, dA/dD over the batch.
+// Deterministic reduction of the workspace partials: dB/dC over channel tiles, dA/dD over (batch, time-warp).
 template <typename T>
 __global__ void selscan_bwd_finish_kernel(const float *__restrict__ ws_bc, const float *__restrict__ ws_ad, T *dBm, T *dCm,
-                                          float *dA, float *dD, int64_t rows, int ntile, int B, int ED) {
+                                          float *dA, float *dD, int64_t rows, int ntile, int nparts, int ED) {
     constexpr int N = kN;
     const int64_t gid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t n_bc = rows * 2 * N;
@@ -402,73 +576,58 @@ __global__ void selscan_bwd_finish_kernel(const float *__restrict__ ws_bc, const
     const int64_t g2 = gid - n_bc;
     if (g2 < int64_t(ED) * (N + 1)) {
         float v = 0.f;
-        for (int bI = 0; bI < B; ++bI) v += ws_ad[int64_t(bI) * ED * (N + 1) + g2];
+        for (int bI = 0; bI < nparts; ++bI) v += ws_ad[int64_t(bI) * ED * (N + 1) + g2];
         const int c = int(g2 / (N + 1)), n = int(g2 % (N + 1));
         if (n < N) dA[int64_t(c) * N + n] = v;
         else dD[c] = v;
     }
 }
 
-static int pick_lpc(int B, int ED, int flags) {
-    (void)B; (void)flags;
-    return ED >= 64 ? 1 : ED >= 32 ? 2 : 4;
-}
+constexpr int kBwdWT = 4;
 
-template <typename T, int LPC> static int launch_bwd_t(BwdParams p, int dtype, void *ws, cudaStream_t st) {
-    constexpr int NW = 2, TC = kChunk, STAGES = 3;
-    using Lay = BwdLayout<T, LPC, NW, TC, STAGES>;
-    auto kern = selscan_bwd_kernel<T, LPC, NW, TC, STAGES>;
+template <typename T> static int launch_bwd_t(BwdParams p, int dtype, void *ws, cudaStream_t st) {
+    constexpr int WT = kBwdWT, STAGES = 2;
+    using Lay = BwdLayout<T, WT, STAGES>;
+    auto kern = selscan_bwd_kernel<T, WT, STAGES>;
     if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Lay::SMEM)),
                            "selscan_bwd smem attribute"))
         return e;
-    const uint64_t rows = uint64_t(p.B) * p.L;
+    const uint64_t rows = uint64_t(p.B) * p.L, nb = p.B, L = p.L;
     p.ntile_c = (p.ED + Lay::CH - 1) / Lay::CH;
     p.ws_bc = static_cast<float *>(ws);
     p.ws_ad = p.ws_bc + rows * p.ntile_c * 2 * kN;
     BwdMaps tm;
     memset(&tm, 0, sizeof(tm));
-    if (int e = make_tmap_2d(&tm.x, p.x, dtype, rows, p.ED, p.x_ld * sizeof(T), TC, Lay::CH)) return e;
-    if (int e = make_tmap_2d(&tm.d, p.delta, dtype, rows, p.ED, p.d_ld * sizeof(T), TC, Lay::CH)) return e;
-    if (int e = make_tmap_2d(&tm.g, p.dout, dtype, rows, p.ED, p.g_ld * sizeof(T), TC, Lay::CH)) return e;
+    if (int e = make_tmap_3d(&tm.x, p.x, dtype, nb, L, p.ED, p.x_ld * sizeof(T), Lay::ST, Lay::CH)) return e;
+    if (int e = make_tmap_3d(&tm.d, p.delta, dtype, nb, L, p.ED, p.d_ld * sizeof(T), Lay::ST, Lay::CH)) return e;
+    if (int e = make_tmap_3d(&tm.g, p.dout, dtype, nb, L, p.ED, p.g_ld * sizeof(T), Lay::ST, Lay::CH)) return e;
     if (p.z)
-        if (int e = make_tmap_2d(&tm.z, p.z, dtype, rows, p.ED, p.z_ld * sizeof(T), TC, Lay::CH)) return e;
-    if (int e = make_tmap_2d(&tm.B, p.Bm, dtype, rows, kN, kN * sizeof(T), TC, kN)) return e;
-    if (int e = make_tmap_2d(&tm.C, p.Cm, dtype, rows, kN, kN * sizeof(T), TC, kN)) return e;
-    if (int e = make_tmap_2d(&tm.odx, p.dx, dtype, rows, p.ED, p.ED * sizeof(T), TC, Lay::CH)) return e;
-    if (int e = make_tmap_2d(&tm.odd, p.ddelta, dtype, rows, p.ED, p.ED * sizeof(T), TC, Lay::CH)) return e;
+        if (int e = make_tmap_3d(&tm.z, p.z, dtype, nb, L, p.ED, p.z_ld * sizeof(T), Lay::ST, Lay::CH)) return e;
+    if (int e = make_tmap_3d(&tm.B, p.Bm, dtype, nb, L, kN, kN * sizeof(T), Lay::ST, kN)) return e;
+    if (int e = make_tmap_3d(&tm.C, p.Cm, dtype, nb, L, kN, kN * sizeof(T), Lay::ST, kN)) return e;
+    if (int e = make_tmap_3d(&tm.odx, p.dx, dtype, nb, L, p.ED, p.ED * sizeof(T), Lay::ST, Lay::CH)) return e;
+    if (int e = make_tmap_3d(&tm.odd, p.ddelta, dtype, nb, L, p.ED, p.ED * sizeof(T), Lay::ST, Lay::CH)) return e;
     if (p.dz)
-        if (int e = make_tmap_2d(&tm.odz, p.dz, dtype, rows, p.ED, p.ED * sizeof(T), TC, Lay::CH)) return e;
+        if (int e = make_tmap_3d(&tm.odz, p.dz, dtype, nb, L, p.ED, p.ED * sizeof(T), Lay::ST, Lay::CH)) return e;
     dim3 grid(p.ntile_c, p.B);
-    kern<<<grid, NW * 32, Lay::SMEM, st>>>(p, tm);
+    kern<<<grid, WT * 32, Lay::SMEM, st>>>(p, tm);
     if (int e = check_cuda(cudaGetLastError(), "selscan_bwd launch")) return e;
     const int64_t work = int64_t(rows) * 2 * kN + int64_t(p.ED) * (kN + 1);
     selscan_bwd_finish_kernel<T><<<unsigned((work + 255) / 256), 256, 0, st>>>(
-        p.ws_bc, p.ws_ad, static_cast<T *>(p.dBm), static_cast<T *>(p.dCm), p.dA, p.dD, int64_t(rows), p.ntile_c, p.B, p.ED);
+        p.ws_bc, p.ws_ad, static_cast<T *>(p.dBm), static_cast<T *>(p.dCm), p.dA, p.dD, int64_t(rows), p.ntile_c, p.B * WT, p.ED);
     return check_cuda(cudaGetLastError(), "selscan_bwd finish launch");
 }
 
-template <typename T> static int launch_bwd_lpc(const BwdParams &p, int dtype, int lpc, void *ws, cudaStream_t st) {
-    switch (lpc) {
-        case 1: return launch_bwd_t<T, 1>(p, dtype, ws, st);
-        case 2: return launch_bwd_t<T, 2>(p, dtype, ws, st);
-        case 4: return launch_bwd_t<T, 4>(p, dtype, ws, st);
-    }
-    set_error("selscan_bwd: lanes-per-channel must be 1, 2 or 4 (got %d)", lpc);
-    return MMI_ERR_ARG;
-}
-
-// worst case over the LPC choices: smallest channel tile = NW*32/4 = 16 channels
 int64_t selscan_bwd_ws_bytes(int B, int L, int ED) {
-    const int64_t ntile_max = (ED + 15) / 16;
-    return (int64_t(B) * L * ntile_max * 2 * kN + int64_t(B) * ED * (kN + 1)) * 4;
+    const int64_t ntile = (ED + 63) / 64;
+    return (int64_t(B) * L * ntile * 2 * kN + int64_t(B) * kBwdWT * ED * (kN + 1)) * 4;
 }
 
 int selscan_bwd_launch(BwdParams p, int dtype, void *ws, cudaStream_t st) {
-    const int lpc = pick_lpc(p.B, p.ED, p.flags);
     switch (dtype) {
-        case MMI_F32: return launch_bwd_lpc<float>(p, dtype, lpc, ws, st);
-        case MMI_BF16: return launch_bwd_lpc<__nv_bfloat16>(p, dtype, lpc, ws, st);
-        case MMI_F16: return launch_bwd_lpc<__half>(p, dtype, lpc, ws, st);
+        case MMI_F32: return launch_bwd_t<float>(p, dtype, ws, st);
+        case MMI_BF16: return launch_bwd_t<__nv_bfloat16>(p, dtype, ws, st);
+        case MMI_F16: return launch_bwd_t<__half>(p, dtype, ws, st);
     }
     set_error("selscan_bwd: unknown dtype %d", dtype);
     return MMI_ERR_ARG;

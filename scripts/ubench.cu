@@ -101,63 +101,60 @@ template <int MODE> __global__ void k_alu(float *out, long long *cyc, float s) {
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
-// shared memory: MODE 0: LDS.128 conflict-free (lane-private 16B); 1: LDS.128 broadcast; 2: STS.128; 3: LDS.32;
-// 4: FFMA2 x8 + LDS.128 x4 per iter (co-issue); 5: FFMA2 x8 + STS.128 x2 + LDS.128 x2
+// shared memory.  MODE 0: LDS.128 lane-private (conflict-free, 512 B/instr); 1: LDS.128 rotated by lane (conflict-free);
+// 2: STS.128; 3: LDS.32 conflict-free; 4: LDS.128 broadcast (all lanes one address); 5: LDS.64 broadcast; 6: LDS.32
+// broadcast; 7: FFMA2 x8 + LDS.128 broadcast x4; 8: FFMA2 x8 + LDS.128 private x2 + STS.128 x2
 template <int MODE> __global__ void k_smem(float *out, long long *cyc, float s) {
     extern __shared__ float4 sm[];
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int i = tid; i < 4 * nt; i += nt) sm[i] = make_float4(i, 1, 2, 3);
     __syncthreads();
-    float4 acc = make_float4(0, 0, 0, 0);
+    float acc = 0.f;
     float r[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) r[i] = tid * 0.001f + i;
     const float a = s, b = 0.5f * s;
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(sm);
     const long long t0 = clock64();
 #pragma unroll 1
     for (int it = 0; it < ITERS; ++it) {
-        if (MODE == 0 || MODE == 1) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int idx = (MODE == 0) ? ((i & 3) * nt + tid) : ((i & 3) * nt + (tid & ~31) + ((it + i) & 31));
-                float4 v = lds128(&sm[idx]);
-                acc.x += v.x;
-                acc.y += v.w;
-            }
-        } else if (MODE == 2) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) sts128(&sm[(i & 3) * nt + tid], make_float4(r[0], r[1], r[2], it));
-        } else if (MODE == 3) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float v = lds32((float *)sm + (i & 3) * nt + tid);
-                acc.x += v;
-            }
-        } else if (MODE == 4 || MODE == 5) {
+        if (MODE == 7 || MODE == 8) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 float2 v = fma2(make_float2(r[2 * i], r[2 * i + 1]), make_float2(a, b), make_float2(b, a));
                 r[2 * i] = v.x;
                 r[2 * i + 1] = v.y;
             }
-            if (MODE == 4) {
+        }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float4 v = lds128(&sm[i * nt + tid]);
-                    acc.x += v.x;
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    sts128(&sm[i * nt + tid], make_float4(r[0], r[1], r[2], it));
-                    float4 v = lds128(&sm[(i + 2) * nt + tid]);
-                    acc.x += v.x;
-                }
+        for (int i = 0; i < 8; ++i) {
+            uint32_t addr;
+            if (MODE == 0 || MODE == 2) addr = base + 16u * ((i & 3) * nt + tid);
+            else if (MODE == 1) addr = base + 16u * ((i & 3) * nt + (tid & ~31) + ((tid + it + i) & 31));
+            else if (MODE == 3) addr = base + 4u * ((i & 3) * nt + tid);
+            else if (MODE == 8) addr = base + 16u * ((i & 1) * nt + tid);
+            else addr = base + 16u * ((i & 3) * nt + (tid & ~31) + ((it + i) & 31));
+            if (MODE == 0 || MODE == 1 || MODE == 4 || (MODE == 7 && i < 4) || (MODE == 8 && i < 2)) {
+                float4 v;
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+                acc += (v.x + v.y) + (v.z + v.w);
+            } else if (MODE == 2 || (MODE == 8 && i >= 2 && i < 4)) {
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr + (MODE == 8 ? 32u * nt : 0u)), "f"(r[0]), "f"(r[1]),
+                             "f"(r[2]), "f"(acc)
+                             : "memory");
+            } else if (MODE == 5) {
+                float2 v;
+                asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+                acc += v.x + v.y;
+            } else if (MODE == 3 || MODE == 6) {
+                float v;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+                acc += v;
             }
         }
     }
     const long long t1 = clock64();
-    float o = acc.x + acc.y;
+    float o = acc;
 #pragma unroll
     for (int i = 0; i < 16; ++i) o += r[i];
     out[blockIdx.x * nt + tid] = o;
@@ -168,7 +165,9 @@ template <int MODE> __global__ void k_smem(float *out, long long *cyc, float s) 
 // MODE 0: st only; 1: ld only; 2: st+ld pairs; 3: FFMA2 x8 + st + ld per iter
 template <int MODE> __global__ void k_tmem(float *out, long long *cyc, float s) {
     __shared__ uint32_t tbase_s;
+    __shared__ float4 scr[4 * 512];
     const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 4 * 512; i += blockDim.x) scr[i] = make_float4(i, 1, 2, 3);
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
             (uint32_t)__cvta_generic_to_shared(&tbase_s)));
@@ -213,13 +212,23 @@ template <int MODE> __global__ void k_tmem(float *out, long long *cyc, float s) 
                 f[2 * i + 1] = v.y;
             }
         }
-        if (MODE == 0 || MODE == 2 || MODE == 3) {
+        if (MODE == 4) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const uint32_t sa = (uint32_t)__cvta_generic_to_shared(scr) + 16u * (i * blockDim.x + tid);
+                float4 v;
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sa));
+                f[0] += (v.x + v.y) + (v.z + v.w);
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sa + 32u * blockDim.x), "f"(f[1]), "f"(f[2]), "f"(f[3]), "f"(f[0]) : "memory");
+            }
+        }
+        if (MODE == 0 || MODE == 2 || MODE == 3 || MODE == 4) {
             asm volatile(
                 "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(ta),
                 "r"(r[0] + it), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
                 "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]));
         }
-        if (MODE == 1 || MODE == 2 || MODE == 3) {
+        if (MODE == 1 || MODE == 2 || MODE == 3 || MODE == 4) {
             uint32_t q[16];
             const uint32_t tb = taddr0 + (uint32_t)(((it + 1) % nslot) * 16);
             asm volatile(
@@ -306,13 +315,17 @@ int main() {
         run("LDS.128 lane-private x8", k_smem<0>, w, 8, sm, out, cyc, sms);
         run("LDS.128 rotated x8", k_smem<1>, w, 8, sm, out, cyc, sms);
         run("STS.128 x8", k_smem<2>, w, 8, sm, out, cyc, sms);
-        run("LDS.32 x8", k_smem<3>, w, 8, sm, out, cyc, sms);
-        run("FFMA2 x8 + LDS.128 x4 (count 12)", k_smem<4>, w, 12, sm, out, cyc, sms);
-        run("FFMA2 x8 + STS.128 x2 + LDS.128 x2 (12)", k_smem<5>, w, 12, sm, out, cyc, sms);
+        run("LDS.32 private x8", k_smem<3>, w, 8, sm, out, cyc, sms);
+        run("LDS.128 broadcast x8", k_smem<4>, w, 8, sm, out, cyc, sms);
+        run("LDS.64 broadcast x8", k_smem<5>, w, 8, sm, out, cyc, sms);
+        run("LDS.32 broadcast x8", k_smem<6>, w, 8, sm, out, cyc, sms);
+        run("FFMA2 x8 + LDS.128 bcast x4 (count 12)", k_smem<7>, w, 12, sm, out, cyc, sms);
+        run("FFMA2 x8 + LDS.128 x2 + STS.128 x2 (12)", k_smem<8>, w, 12, sm, out, cyc, sms);
         run("tcgen05.st x16 (count 1)", k_tmem<0>, w, 1, 0, out, cyc, sms);
         run("tcgen05.ld x16 (count 1)", k_tmem<1>, w, 1, 0, out, cyc, sms);
         run("tcgen05.st+ld x16 (count 2)", k_tmem<2>, w, 2, 0, out, cyc, sms);
         run("FFMA2 x8 + tcgen05 st+ld (count 10)", k_tmem<3>, w, 10, 0, out, cyc, sms);
+        run("tcgen05 st+ld + LDS.128x2 + STS.128x2 (6)", k_tmem<4>, w, 6, 0, out, cyc, sms);
     }
     return 0;
 }
