@@ -92,6 +92,55 @@ template <int N> __device__ __forceinline__ void bulk_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
+// Shared-memory loads the compiler may hoist above earlier plain stores.  The scan kernels update their tiles in place
+// (row t is read, then overwritten with an output); nvcc cannot prove that the store to row t does not alias the load of
+// row t+1, so with plain loads every step starts with a load burst it then waits on.  `asm volatile` without a memory
+// clobber keeps each load (no CSE across the in-place update, never deleted, ordered against the other volatile asm) but
+// lets it move across plain stores; real producer -> consumer hand-offs between phases all sit behind __syncthreads /
+// __syncwarp / tcgen05.wait, which are compiler barriers.
+__device__ __forceinline__ float4 lds_f4(const void *p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+    return v;
+}
+__device__ __forceinline__ float2 lds_f2(const void *p) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(smem_u32(p)));
+    return v;
+}
+__device__ __forceinline__ float lds_f1(const void *p) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(const void *p) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)));
+    return v;
+}
+__device__ __forceinline__ unsigned short lds_u16(const void *p) {
+    unsigned short v;
+    asm volatile("ld.shared.b16 %0, [%1];" : "=h"(v) : "r"(smem_u32(p)));
+    return v;
+}
+// one tile element / two adjacent tile elements as fp32
+template <typename T> __device__ __forceinline__ float lds_elem(const T *p);
+template <> __device__ __forceinline__ float lds_elem<float>(const float *p) { return lds_f1(p); }
+template <> __device__ __forceinline__ float lds_elem<__nv_bfloat16>(const __nv_bfloat16 *p) {
+    return __uint_as_float(uint32_t(lds_u16(p)) << 16);
+}
+template <> __device__ __forceinline__ float lds_elem<__half>(const __half *p) { return __half2float(__ushort_as_half(lds_u16(p))); }
+template <typename T> __device__ __forceinline__ float2 lds_pair(const T *p);
+template <> __device__ __forceinline__ float2 lds_pair<float>(const float *p) { return lds_f2(p); }
+template <> __device__ __forceinline__ float2 lds_pair<__nv_bfloat16>(const __nv_bfloat16 *p) {
+    const uint32_t w = lds_u32(p);
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+template <> __device__ __forceinline__ float2 lds_pair<__half>(const __half *p) {
+    const uint32_t w = lds_u32(p);
+    return __half22float2(*reinterpret_cast<const __half2 *>(&w));
+}
+
 // streaming global stores (outputs are never re-read by the kernel that writes them)
 __device__ __forceinline__ void st_cs(float *p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void st_cs(__nv_bfloat16 *p, __nv_bfloat16 v) {

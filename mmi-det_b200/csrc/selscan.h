@@ -5,7 +5,8 @@
 
 namespace mmi {
 
-constexpr int kChunk = 16;  // state-checkpoint interval in timesteps == the chunk one warp scans per super-tile
+constexpr int kChunk = 16;     // state-checkpoint interval in timesteps == the chunk one backward warp scans per super-tile
+constexpr int kFwdChunk = 16;  // chunk one forward warp scans per super-tile (a multiple of kChunk)
 
 struct FwdParams {
     const void *x, *delta, *z, *Bm, *Cm;

@@ -39,9 +39,10 @@ struct FwdMaps {
 };
 
 constexpr int kBlk = 8;  // steps per branch-free block of sweep B
+static_assert(kChunk % kBlk == 0, "sweep B writes a checkpoint at block starts");
 
 template <typename T, int WC, int WT, int STAGES> struct FwdLayout {
-    static constexpr int N = kN, TC = kChunk, ST = WT * TC, CH = 32 * WC, NW = WC * WT;
+    static constexpr int N = kN, TC = kFwdChunk, ST = WT * TC, CH = 32 * WC, NW = WC * WT;
     static constexpr size_t TILE_BYTES = size_t(ST) * CH * sizeof(T);
     static constexpr size_t BCT_BYTES = size_t(ST) * N * sizeof(T);
     static constexpr size_t STAGE_BYTES = 3 * TILE_BYTES + 2 * BCT_BYTES;  // x | delta | z (-> out) | B | C
@@ -97,7 +98,7 @@ __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, 
     float *bc32 = reinterpret_cast<float *>(smem + Lay::BC32_OFF) + warp * 2 * TC * N;
 
     const int L = p.L, ED = p.ED;
-    const int ntiles = (L + ST - 1) / ST, nchk = (L + TC - 1) / TC;
+    const int ntiles = (L + ST - 1) / ST, nchk = (L + kChunk - 1) / kChunk;
     const int cl = wc * 32 + lane, tb = wt * TC;
 
     auto issue = [&](int s, int ti) {  // one elected thread: the 5 tile loads of a super-tile arrive on full[s]
@@ -223,12 +224,6 @@ __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, 
             for (int k = 0; k < 4; ++k)
                 cout[k * 32] = make_float4(hlast[2 * k].x, hlast[2 * k].y, hlast[2 * k + 1].x, hlast[2 * k + 1].y);
         }
-        if (p.chk && active && t0 + tb < L) {  // checkpoint = state entering step t0 + tb
-            float4 *ck = reinterpret_cast<float4 *>(p.chk + ((int64_t(b) * nchk + (t0 + tb) / TC) * ED + c) * N);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) __stcs(ck + k, make_float4(h2[2 * k].x, h2[2 * k].y, h2[2 * k + 1].x, h2[2 * k + 1].y));
-        }
-
         // ---- sweep B: the scan proper.  kBlk consecutive timesteps, branch-free and software-pipelined in three
         // phases so that independent work of neighbouring steps (LDS, MUFU, gate) overlaps the serial h chain:
         //   1  loads + per-step scalars (decay base r; delta*x; gate factor z*sigmoid(z))
@@ -236,6 +231,11 @@ __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, 
         //   3  D skip, gate, store into the output tile
 #pragma unroll 1
         for (int ub = 0; ub < TC; ub += kBlk) {
+            if (p.chk && active && ub % kChunk == 0 && t0 + tb + ub < L) {  // checkpoint = state entering step t0 + tb + ub
+                float4 *ck = reinterpret_cast<float4 *>(p.chk + ((int64_t(b) * nchk + (t0 + tb + ub) / kChunk) * ED + c) * N);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) __stcs(ck + k, make_float4(h2[2 * k].x, h2[2 * k].y, h2[2 * k + 1].x, h2[2 * k + 1].y));
+            }
             float xv[kBlk], dvv[kBlk], gz[kBlk], yv[kBlk];
 #pragma unroll
             for (int u = 0; u < kBlk; ++u) {
