@@ -589,9 +589,15 @@ template <typename T> static int launch_bwd_t(BwdParams p, int dtype, void *ws, 
     constexpr int WT = kBwdWT, STAGES = 2;
     using Lay = BwdLayout<T, WT, STAGES>;
     auto kern = selscan_bwd_kernel<T, WT, STAGES>;
-    if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Lay::SMEM)),
-                           "selscan_bwd smem attribute"))
-        return e;
+    static thread_local int attr_dev = -1;  // the opt-in is per device and sticky: set it once, not on every launch
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (attr_dev != dev) {
+        if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Lay::SMEM)),
+                               "selscan_bwd smem attribute"))
+            return e;
+        attr_dev = dev;
+    }
     const uint64_t rows = uint64_t(p.B) * p.L, nb = p.B, L = p.L;
     p.ntile_c = (p.ED + Lay::CH - 1) / Lay::CH;
     p.ws_bc = static_cast<float *>(ws);

@@ -346,9 +346,15 @@ template <typename T, int WC, int WT, int STAGES> static int launch_fwd_t(const 
     if (int e = make_tmap_3d(&tm.B, p.Bm, dtype, nb, L, kN, kN * sizeof(T), Lay::ST, kN)) return e;
     if (int e = make_tmap_3d(&tm.C, p.Cm, dtype, nb, L, kN, kN * sizeof(T), Lay::ST, kN)) return e;
     if (int e = make_tmap_3d(&tm.o, p.out, dtype, nb, L, p.ED, p.o_ld * sizeof(T), Lay::ST, Lay::CH)) return e;
-    if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Lay::SMEM)),
-                           "selscan_fwd smem attribute"))
-        return e;
+    static thread_local int attr_dev = -1;  // the opt-in is per device and sticky: set it once, not on every launch
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (attr_dev != dev) {
+        if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Lay::SMEM)),
+                               "selscan_fwd smem attribute"))
+            return e;
+        attr_dev = dev;
+    }
     const unsigned gx = (p.ED + Lay::CH - 1) / Lay::CH;
     kern<<<dim3(gx, p.B), Lay::NW * 32, Lay::SMEM, st>>>(p, tm);
     return check_cuda(cudaGetLastError(), "selscan_fwd launch");

@@ -1,0 +1,242 @@
+"""Host-side mirror of models/mamba.py for the B200 path, plus the VIS+IR fusion module and the plug-in helper.
+
+Same class names, constructor signatures, parameter names and shapes as the reference, so a reference state_dict loads
+unchanged and pickled / deep-copied modules behave the same (no ctypes handles or streams are stored on a
+module; the library is loaded lazily by the operator layer):
+
+    MambaConfig      models/mamba.py:30-54     RMSNorm        models/mamba.py:356-366
+    MambaBlock       models/mamba.py:117-353   ResidualBlock  models/mamba.py:89-115      Mamba   models/mamba.py:56-87
+
+What differs is only where the arithmetic runs: `MambaBlock.selective_scan` and the SiLU gate (models/mamba.py:212-233,
+184-186) go through the fused sm_100a kernels (ops.selective_scan); the four projections stay nn.Linear (cuBLAS), the
+depthwise causal conv stays nn.Conv1d (cuDNN), as the north_star prescribes.  Unlike the reference the block is
+half/bf16-clean: inputs of any float dtype are accepted and the input dtype is returned.
+
+`MambaFusion` is the cross-modal block the north_star names (the reference ships none): it keeps the I/O
+contract of the reference's `GPT` fusion transformer (models/common.py:1270-1370: ctor called with d_model only,
+forward([rgb, ir]) -> (rgb_out, ir_out) with input shapes preserved, VIS tokens first then IR tokens) so that
+`install(fusion=True)` can bind it to the YAML name `GPT` that the unchanged parse_model looks up (models/yolo_test.py:560,
+600-602).  CUDA only: there is no CPU fallback anywhere in this package."""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Union
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+
+@dataclass
+class MambaConfig:
+    d_model: int
+    n_layers: int
+    dt_rank: Union[int, str] = "auto"
+    d_state: int = 16
+    expand_factor: int = 2
+    d_conv: int = 4
+    dt_min: float = 0.001
+    dt_max: float = 0.1
+    dt_init: str = "random"
+    dt_scale: float = 1.0
+    dt_init_floor = 1e-4
+    bias: bool = False
+    conv_bias: bool = True
+    pscan: bool = True  # kept for signature compatibility; both settings run the same fused kernel
+
+    def __post_init__(self):
+        self.d_inner = self.expand_factor * self.d_model
+        if self.dt_rank == "auto":
+            self.dt_rank = math.ceil(self.d_model / 16)
+
+
+class RMSNorm(nn.Module):
+    def __init__(self, d_model: int, eps: float = 1e-5):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(d_model))
+
+    def forward(self, x):
+        return x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + self.eps) * self.weight
+
+
+class MambaBlock(nn.Module):
+    def __init__(self, config: MambaConfig):
+        super().__init__()
+        self.config = config
+        c = config
+        self.in_proj = nn.Linear(c.d_model, 2 * c.d_inner, bias=c.bias)
+        self.conv1d = nn.Conv1d(c.d_inner, c.d_inner, kernel_size=c.d_conv, bias=c.conv_bias, groups=c.d_inner,
+                                padding=c.d_conv - 1)
+        self.x_proj = nn.Linear(c.d_inner, c.dt_rank + 2 * c.d_state, bias=False)
+        self.dt_proj = nn.Linear(c.dt_rank, c.d_inner, bias=True)
+        # same initial distribution as the reference (models/mamba.py:137-160): dt weights ~ U(+-dt_rank^-0.5 * scale) or
+        # constant; dt bias = softplus^-1 of a log-uniform step in [dt_min, dt_max]; A = -(1..N) per channel; D = 1
+        std = c.dt_rank ** -0.5 * c.dt_scale
+        if c.dt_init == "constant":
+            nn.init.constant_(self.dt_proj.weight, std)
+        elif c.dt_init == "random":
+            nn.init.uniform_(self.dt_proj.weight, -std, std)
+        else:
+            raise NotImplementedError(c.dt_init)
+        lo, hi = math.log(c.dt_min), math.log(c.dt_max)
+        dt = torch.exp(torch.rand(c.d_inner) * (hi - lo) + lo).clamp(min=c.dt_init_floor)
+        with torch.no_grad():
+            self.dt_proj.bias.copy_(dt + torch.log(-torch.expm1(-dt)))
+        self.A_log = nn.Parameter(torch.log(torch.arange(1, c.d_state + 1, dtype=torch.float32).repeat(c.d_inner, 1)))
+        self.D = nn.Parameter(torch.ones(c.d_inner))
+        self.out_proj = nn.Linear(c.d_inner, c.d_model, bias=c.bias)
+
+    # -- the hot path -----------------------------------------------------------------------------------------
+    def selective_scan(self, x, delta, A, B, C, D, z=None):
+        """models/mamba.py:212-233 (and :235-265, same maths) on the fused kernel; `z` additionally fuses the gate."""
+        return ops.selective_scan(x, delta, A, B, C, D, z=z)
+
+    selective_scan_seq = selective_scan
+
+    def ssm(self, x, z=None):
+        c = self.config
+        A = -torch.exp(self.A_log.float())
+        dbc = self.x_proj(x)
+        delta, B, C = torch.split(dbc, [c.dt_rank, c.d_state, c.d_state], dim=-1)
+        delta = F.softplus(self.dt_proj(delta))
+        return self.selective_scan(x, delta, A, B, C, self.D.float(), z=z)
+
+    def forward(self, x):
+        L = x.shape[1]
+        xz = self.in_proj(x)
+        xs, z = xz.chunk(2, dim=-1)  # views of one GEMM output: passed to the kernel by row pitch, never copied
+        xs = F.silu(self.conv1d(xs.transpose(1, 2))[:, :, :L].transpose(1, 2))
+        y = self.ssm(xs, z=z)  # = ssm(x) * silu(z): the gate of models/mamba.py:184-186 is fused into the scan
+        return self.out_proj(y.to(xz.dtype))
+
+    # -- single-token recurrent inference (models/mamba.py:289-353); unused by the detector, kept as plain torch ----
+    def step(self, x, cache):
+        h, inputs = cache
+        xz = self.in_proj(x)
+        xs, z = xz.chunk(2, dim=1)
+        xc = xs.unsqueeze(2)
+        xs = F.silu(self.conv1d(torch.cat([inputs, xc], dim=2))[:, :, self.config.d_conv - 1])
+        y, h = self.ssm_step(xs, h)
+        out = self.out_proj(y * F.silu(z))
+        return out, (h, torch.cat([inputs[:, :, 1:], xc], dim=2))
+
+    def ssm_step(self, x, h):
+        c = self.config
+        A = -torch.exp(self.A_log.float())
+        delta, B, C = torch.split(self.x_proj(x), [c.dt_rank, c.d_state, c.d_state], dim=-1)
+        delta = F.softplus(self.dt_proj(delta))
+        dA = torch.exp(delta.unsqueeze(-1) * A)
+        dBx = delta.unsqueeze(-1) * B.unsqueeze(1) * x.unsqueeze(-1)
+        if h is None:
+            h = torch.zeros(x.size(0), c.d_inner, c.d_state, device=dA.device, dtype=dA.dtype)
+        h = dA * h + dBx
+        y = (h @ C.unsqueeze(-1)).squeeze(2) + self.D.float() * x
+        return y, h
+
+
+class ResidualBlock(nn.Module):
+    def __init__(self, config: MambaConfig):
+        super().__init__()
+        self.mixer = MambaBlock(config)
+        self.norm = RMSNorm(config.d_model)
+
+    def forward(self, x):
+        return self.mixer(self.norm(x)) + x
+
+    def step(self, x, cache):
+        out, cache = self.mixer.step(self.norm(x), cache)
+        return out + x, cache
+
+
+class Mamba(nn.Module):
+    def __init__(self, config: MambaConfig):
+        super().__init__()
+        self.config = config
+        self.layers = nn.ModuleList([ResidualBlock(config) for _ in range(config.n_layers)])
+
+    def forward(self, x):
+        for layer in self.layers:
+            x = layer(x)
+        return x
+
+    def step(self, x, caches):
+        for i, layer in enumerate(self.layers):
+            x, caches[i] = layer.step(x, caches[i])
+        return x, caches
+
+
+class MambaFusion(nn.Module):
+    """Cross-modal fusion with the `GPT` contract (models/common.py:1270-1370).
+
+    forward([rgb, ir]) with rgb, ir (B, C, H, W): both maps are flattened to tokens at FULL resolution (no 8x8 pooling:
+    L = H*W per modality, i.e. L = 6400 at P3 / 640 px, the BASELINE shape), concatenated along the sequence axis as
+    VIS tokens then IR tokens (models/common.py:1340-1343), run through `n_layer` ResidualBlocks (RMSNorm -> MambaBlock ->
+    + x, models/mamba.py:89-102) so the state carried out of the VIS half conditions the IR half, and split back.
+    `block_cls` lets a test build the very same module on the reference's pure-PyTorch ResidualBlock (the logits oracle).
+    Extra ctor arguments of GPT (h, block_exp, vert_anchors, ... ) are accepted and ignored."""
+
+    def __init__(self, d_model, h=8, block_exp=4, n_layer=1, vert_anchors=8, horz_anchors=8, embd_pdrop=0.1, attn_pdrop=0.1,
+                 resid_pdrop=0.1, block_cls=None, config_cls=None):
+        super().__init__()
+        cfg = (config_cls or MambaConfig)(d_model=d_model, n_layers=n_layer)
+        self.n_embd = d_model
+        self.layers = nn.ModuleList([(block_cls or ResidualBlock)(cfg) for _ in range(n_layer)])
+
+    def forward(self, x):
+        rgb, ir = x[0], x[1]
+        B, C, H, W = rgb.shape
+        tok = torch.cat([rgb.flatten(2), ir.flatten(2)], dim=2).transpose(1, 2)  # (B, 2HW, C), VIS then IR
+        for layer in self.layers:
+            tok = layer(tok)
+        out = tok.transpose(1, 2).reshape(B, C, 2, H, W)
+        return out[:, :, 0].contiguous(), out[:, :, 1].contiguous()
+
+
+def install(ref_models=None, scan=True, pscan=True, ffm=True, fusion=False):
+    """Bind the B200 path into an imported, UNMODIFIED reference tree -- the stubs INTEGRATION.md shows:
+
+        import models.mamba, models.common, models.yolo_test      # the reference, untouched
+        import mmidet_b200.mamba as M; M.install(fusion=True)
+
+    scan    MambaBlock.selective_scan / selective_scan_seq  -> fused kernel (class attribute patch; ctor untouched)
+    pscan   models.mamba.pscan (= PScan.apply)               -> mmidet_b200.pscan.pscan
+    ffm     models.common.extract_frequency2, Seperation_loss -> mmidet_b200.ffm
+    fusion  models.yolo_test.GPT                              -> MambaFusion (YAML rows naming GPT then build it)
+    Returns the list of replaced attributes so a caller can restore them."""
+    import importlib
+
+    from . import ffm as _ffm
+    from . import pscan as _pscan
+    saved = []
+
+    def mod(name):
+        return importlib.import_module(name) if ref_models is None else getattr(ref_models, name.split(".")[-1])
+
+    def swap(obj, attr, new):
+        saved.append((obj, attr, getattr(obj, attr)))
+        setattr(obj, attr, new)
+
+    if scan or pscan:
+        mm = mod("models.mamba")
+        if scan:
+            fused = lambda self, x, delta, A, B, C, D: ops.selective_scan(x, delta, A, B, C, D)  # noqa: E731
+            swap(mm.MambaBlock, "selective_scan", fused)
+            swap(mm.MambaBlock, "selective_scan_seq", fused)
+        if pscan:
+            swap(mm, "pscan", _pscan.pscan)
+    if ffm:
+        mc = mod("models.common")
+        swap(mc, "extract_frequency2", _ffm.extract_frequency2)
+        swap(mc, "Seperation_loss", _ffm.separation_loss)
+    if fusion:
+        swap(mod("models.yolo_test"), "GPT", MambaFusion)
+    return saved
+
+
+def uninstall(saved):
+    for obj, attr, old in reversed(saved):
+        setattr(obj, attr, old)

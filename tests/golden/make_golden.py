@@ -120,9 +120,69 @@ def gen_ffm():
     save("seploss", M=M, loss=C.Seperation_loss(M))
 
 
+
+
+def gen_fusion():
+    """MambaFusion (our GPT-contract wrapper, pure torch glue) built on the REFERENCE's ResidualBlock / MambaConfig:
+    the logits oracle of the cross-modal block (SURVEY 7.3 'what the fusion module is')."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from mmidet_b200.mamba import MambaFusion
+    torch.manual_seed(1)
+    fus = MambaFusion(16, n_layer=2, block_cls=ResidualBlock, config_cls=MambaConfig)
+    rgb = torch.randn(2, 16, 6, 5, requires_grad=True)
+    ir = torch.randn(2, 16, 6, 5, requires_grad=True)
+    o_rgb, o_ir = fus([rgb, ir])
+    g1, g2 = torch.randn_like(o_rgb), torch.randn_like(o_ir)
+    grgb, gir = torch.autograd.grad([o_rgb, o_ir], [rgb, ir], [g1, g2])
+    arrs = {"sd." + k: v for k, v in fus.state_dict().items()}
+    save("fusion_block", rgb=rgb, ir=ir, o_rgb=o_rgb, o_ir=o_ir, g_rgb=g1, g_ir=g2, d_rgb=grgb, d_ir=gir, **arrs)
+
+
+def gen_detector():
+    """Two-stream YOLOv5s (BASELINE configs[1], reduced to 160x160 so the fixture stays small): the UNMODIFIED
+    models/yolo_test.py Model / parse_model / YAML with `GPT` bound to MambaFusion on reference blocks.  Stored: the
+    inputs and outputs of every fusion call site (the boundary our CUDA path must reproduce) and the Detect output
+    (for the record; the detector itself cannot travel to the GPU box)."""
+    import yaml
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from mmidet_b200.mamba import MambaFusion
+    import models.yolo_test as Y
+    Y.GPT = lambda d_model, *a, **k: MambaFusion(d_model, n_layer=1, block_cls=ResidualBlock, config_cls=MambaConfig)
+    # parse_model compares `m is GPT` after eval()-ing the YAML name, so the bound object must be the same one
+    gpt = Y.GPT
+    cfg = yaml.safe_load(open(os.path.join(REF, "models/transformer/yolov5l_fusion_transformer_M3FD.yaml")))
+    cfg["depth_multiple"], cfg["width_multiple"], cfg["nc"] = 0.33, 0.50, 6
+    torch.manual_seed(0)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = Y.Model(cfg, ch=3, nc=6).eval()
+    fus = [m for m in model.modules() if isinstance(m, MambaFusion)]
+    # weights of the fusion blocks are re-drawn from one seed per call site, so the GPU-side test can rebuild them from
+    # the seed (same torch build, same constructor draw order) and the fixture only has to carry checksums
+    for i, m in enumerate(fus):
+        torch.manual_seed(1000 + i)
+        m.load_state_dict(MambaFusion(m.n_embd, n_layer=1, block_cls=ResidualBlock, config_cls=MambaConfig).state_dict())
+    cap = []
+    for m in fus:
+        m.register_forward_hook(lambda mod, inp, out: cap.append((inp[0][0].detach(), inp[0][1].detach(), out[0].detach(),
+                                                                   out[1].detach())))
+    g = torch.Generator().manual_seed(2)
+    rgb, ir = torch.rand(1, 3, 96, 96, generator=g), torch.rand(1, 3, 96, 96, generator=g)
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        out = model(rgb, ir)
+    det = out[0][0] if isinstance(out[0], (tuple, list)) else out[0]
+    arrs = {"detect": det, "n_sites": np.int64(len(fus))}
+    for i, (m, (a, b, oa, ob)) in enumerate(zip(fus, cap)):
+        arrs.update({f"f{i}.rgb": a, f"f{i}.ir": b, f"f{i}.o_rgb": oa, f"f{i}.o_ir": ob, f"f{i}.d_model": np.int64(m.n_embd)})
+        arrs[f"f{i}.wsum"] = np.array([[float(v.double().sum()), float(v.double().abs().sum())]
+                                        for _, v in sorted(m.state_dict().items())])
+    print("fusion sites:", [tuple(c[0].shape) for c in cap], "detect", tuple(det.shape), "GPT bound:", gpt is Y.GPT)
+    save("detector_fusion", **arrs)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
-    gen_pscan()
-    gen_selscan()
-    gen_block()
-    gen_ffm()
+    todo = sys.argv[1:] or ["pscan", "selscan", "block", "ffm", "fusion", "detector"]
+    for name in todo:
+        globals()["gen_" + name]()

@@ -1,0 +1,58 @@
+"""CPU tests of the plug-in helper: mmidet_b200.mamba.install binds the B200 path into a reference-shaped module tree
+by name and uninstall restores it.  A stand-in tree is used (the real reference does not travel to CI)."""
+import types
+
+import torch
+
+
+def _fake_tree():
+    class MambaBlock:  # same attribute names the reference class exposes
+        def selective_scan(self, *a):
+            return "ref_scan"
+
+        def selective_scan_seq(self, *a):
+            return "ref_seq"
+
+    mamba = types.SimpleNamespace(MambaBlock=MambaBlock, pscan="ref_pscan")
+    common = types.SimpleNamespace(extract_frequency2="ref_ffm", Seperation_loss="ref_sep")
+    yolo = types.SimpleNamespace(GPT="ref_gpt")
+    return types.SimpleNamespace(mamba=mamba, common=common, yolo_test=yolo)
+
+
+def test_install_and_uninstall():
+    from mmidet_b200 import ffm, mamba as M, pscan
+    t = _fake_tree()
+    saved = M.install(ref_models=t, fusion=True)
+    assert t.mamba.pscan is pscan.pscan
+    assert t.common.extract_frequency2 is ffm.extract_frequency2
+    assert t.common.Seperation_loss is ffm.separation_loss
+    assert t.yolo_test.GPT is M.MambaFusion
+    assert t.mamba.MambaBlock.selective_scan is t.mamba.MambaBlock.selective_scan_seq
+    # the patched method is the fused operator: CPU tensors must raise, never fall back
+    try:
+        t.mamba.MambaBlock().selective_scan(torch.randn(1, 8, 16), torch.randn(1, 8, 16), torch.randn(16, 16),
+                                            torch.randn(1, 8, 16), torch.randn(1, 8, 16), torch.randn(16))
+        raise AssertionError("expected RuntimeError")
+    except RuntimeError:
+        pass
+    M.uninstall(saved)
+    assert t.mamba.pscan == "ref_pscan" and t.yolo_test.GPT == "ref_gpt" and t.common.extract_frequency2 == "ref_ffm"
+    assert t.mamba.MambaBlock().selective_scan() == "ref_scan"
+
+
+def test_state_dict_layout_matches_reference(golden):
+    """parameter names and shapes of ResidualBlock == the reference's (tests/golden/mamba_block.npz carries its state_dict)."""
+    from mmidet_b200.mamba import MambaConfig, ResidualBlock
+    g = golden("mamba_block")
+    ref = {k[3:]: v.shape for k, v in g.items() if k.startswith("sd.")}
+    ours = {k: tuple(v.shape) for k, v in ResidualBlock(MambaConfig(d_model=16, n_layers=1)).state_dict().items()}
+    assert ours == {k: tuple(s) for k, s in ref.items()}
+
+
+def test_fusion_contract_shapes_on_meta():
+    """GPT contract (models/common.py:1270-1370): ctor takes d_model (+ ignored extras), token order is VIS then IR."""
+    from mmidet_b200.mamba import MambaFusion
+    fus = MambaFusion(32, 8, 4, 1, 8, 8, 0.1, 0.1, 0.1)
+    assert fus.n_embd == 32 and len(fus.layers) == 1
+    names = {k.split(".")[3] for k in fus.state_dict() if k.startswith("layers.0.mixer.")}
+    assert names >= {"A_log", "D", "in_proj", "conv1d", "x_proj", "dt_proj", "out_proj"}
