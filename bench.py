@@ -98,7 +98,7 @@ def cpu_sample(nthreads=None, seconds_hint=12.0):
     import numpy as np
     from oracle import oracle as O
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    os.environ["OMP_NUM_THREADS"] = str(cores)  # torchrun exports OMP_NUM_THREADS=1 to its workers
     L, ED, N = WORKLOAD["L"], WORKLOAD["ED"], WORKLOAD["N"]
     Bs = 1
     rng = np.random.default_rng(0)
@@ -109,7 +109,9 @@ def cpu_sample(nthreads=None, seconds_hint=12.0):
     dout = rng.standard_normal((Bs, L, ED)).astype(np.float32)
     A = -np.tile(np.arange(1, N + 1, dtype=np.float32), (ED, 1))
     D = np.ones(ED, np.float32)
-    O.lib()
+    ol = O.lib()
+    ol.oracle_set_threads(cores)  # the env var is only read when libgomp initialises; set it explicitly as well
+    cores = int(ol.oracle_max_threads())
     fb, bb = alg_bytes(Bs, L, ED, N, 4)
 
     def once():

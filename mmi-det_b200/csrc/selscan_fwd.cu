@@ -41,8 +41,8 @@ struct FwdMaps {
 constexpr int kBlk = 8;  // steps per branch-free block of sweep B
 static_assert(kChunk % kBlk == 0, "sweep B writes a checkpoint at block starts");
 
-template <typename T, int WC, int WT, int STAGES> struct FwdLayout {
-    static constexpr int N = kN, TC = kFwdChunk, ST = WT * TC, CH = 32 * WC, NW = WC * WT;
+template <typename T, int WC, int WT, int STAGES, int TCH> struct FwdLayout {
+    static constexpr int N = kN, TC = TCH, ST = WT * TC, CH = 32 * WC, NW = WC * WT;
     static constexpr size_t TILE_BYTES = size_t(ST) * CH * sizeof(T);
     static constexpr size_t BCT_BYTES = size_t(ST) * N * sizeof(T);
     static constexpr size_t STAGE_BYTES = 3 * TILE_BYTES + 2 * BCT_BYTES;  // x | delta | z (-> out) | B | C
@@ -85,10 +85,11 @@ __device__ __forceinline__ void load16(const float *p, float2 (&v)[8]) {  // 16 
     }
 }
 
-template <typename T, int WC, int WT, int STAGES, bool GEOM, bool HAS_Z>
+template <typename T, int WC, int WT, int STAGES, int TCH, bool GEOM, bool HAS_Z>
 __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, unsigned char *smem, const float2 (&A2p)[8],
                                          float A2base, float Dd, int c0, int b, int wc, int wt, int lane, int c, bool active) {
-    using Lay = FwdLayout<T, WC, WT, STAGES>;
+    using Lay = FwdLayout<T, WC, WT, STAGES, TCH>;
+    static_assert(TCH % kBlk == 0, "chunks are scanned in blocks of kBlk steps");
     constexpr int N = kN, TC = Lay::TC, ST = Lay::ST, CH = Lay::CH, NW = Lay::NW;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + Lay::BAR_OFF);
     float4 *sumE = reinterpret_cast<float4 *>(smem + Lay::SUM_OFF) + (wt * WC + wc) * 4 * 32 + lane;  // [k4 * 32]
@@ -231,7 +232,7 @@ __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, 
         //   3  D skip, gate, store into the output tile
 #pragma unroll 1
         for (int ub = 0; ub < TC; ub += kBlk) {
-            if (p.chk && active && ub % kChunk == 0 && t0 + tb + ub < L) {  // checkpoint = state entering step t0 + tb + ub
+            if (p.chk && active && (tb + ub) % kChunk == 0 && t0 + tb + ub < L) {  // checkpoint = state entering step t0 + tb + ub
                 float4 *ck = reinterpret_cast<float4 *>(p.chk + ((int64_t(b) * nchk + (t0 + tb + ub) / kChunk) * ED + c) * N);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) __stcs(ck + k, make_float4(h2[2 * k].x, h2[2 * k].y, h2[2 * k + 1].x, h2[2 * k + 1].y));
@@ -289,9 +290,9 @@ __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, 
     }
 }
 
-template <typename T, int WC, int WT, int STAGES>
+template <typename T, int WC, int WT, int STAGES, int TCH>
 __global__ void __launch_bounds__(WC *WT * 32) selscan_fwd_kernel(const FwdParams p, const __grid_constant__ FwdMaps tm) {
-    using Lay = FwdLayout<T, WC, WT, STAGES>;
+    using Lay = FwdLayout<T, WC, WT, STAGES, TCH>;
     constexpr int N = kN, CH = Lay::CH;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + Lay::BAR_OFF);
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(WC *WT * 32) selscan_fwd_kernel(const FwdParam
     const bool geom = __syncthreads_and(ok);  // also publishes the mbarrier inits
     const bool has_z = p.z != nullptr;
 
-#define MMI_FWD_BODY(G, Z) fwd_body<T, WC, WT, STAGES, G, Z>(p, tm, smem, A2p, A2base, Dd, c0, b, wc, wt, lane, c, active)
+#define MMI_FWD_BODY(G, Z) fwd_body<T, WC, WT, STAGES, TCH, G, Z>(p, tm, smem, A2p, A2base, Dd, c0, b, wc, wt, lane, c, active)
     if (geom) {
         if (has_z) MMI_FWD_BODY(true, true);
         else MMI_FWD_BODY(true, false);
@@ -333,9 +334,10 @@ __global__ void __launch_bounds__(WC *WT * 32) selscan_fwd_kernel(const FwdParam
 #undef MMI_FWD_BODY
 }
 
-template <typename T, int WC, int WT, int STAGES> static int launch_fwd_t(const FwdParams &p, int dtype, cudaStream_t st) {
-    using Lay = FwdLayout<T, WC, WT, STAGES>;
-    auto kern = selscan_fwd_kernel<T, WC, WT, STAGES>;
+template <typename T, int WC, int WT, int STAGES, int TCH = kFwdChunk>
+static int launch_fwd_t(const FwdParams &p, int dtype, cudaStream_t st) {
+    using Lay = FwdLayout<T, WC, WT, STAGES, TCH>;
+    auto kern = selscan_fwd_kernel<T, WC, WT, STAGES, TCH>;
     FwdMaps tm;
     memset(&tm, 0, sizeof(tm));
     const uint64_t nb = p.B, L = p.L;
@@ -367,6 +369,9 @@ int selscan_fwd_launch(const FwdParams &p, int dtype, cudaStream_t st) {
         case 1: return launch_fwd_t<T, 2, 4, 3>(p, dtype, st);     \
         case 2: return launch_fwd_t<T, 1, 8, 2>(p, dtype, st);     \
         case 3: return launch_fwd_t<T, 1, 2, 4>(p, dtype, st);     \
+        case 4: return launch_fwd_t<T, 1, 8, 3, 8>(p, dtype, st);  \
+        case 5: return launch_fwd_t<T, 1, 8, 4, 8>(p, dtype, st);  \
+        case 6: return launch_fwd_t<T, 2, 8, 2, 8>(p, dtype, st);  \
         default: return launch_fwd_t<T, 1, 4, 3>(p, dtype, st);    \
     }
     switch (dtype) {

@@ -188,3 +188,15 @@ void SFX(oracle_selscan_bwd)(const real *x, const real *delta, const real *z, co
     for (int i = 0; i < ED; ++i) dD[i] = (real)accD[i];
     free(accB); free(accC); free(accA); free(accD);
 }
+
+/* thread control for the timed CPU-baseline legs of bench.py (torchrun exports OMP_NUM_THREADS=1 to its workers) */
+#ifndef ORACLE_F64 /* this file is compiled twice (f32, f64); define the helpers once */
+#ifdef _OPENMP
+#include <omp.h>
+void oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int oracle_max_threads(void) { return omp_get_max_threads(); }
+#else
+void oracle_set_threads(int n) { (void)n; }
+int oracle_max_threads(void) { return 1; }
+#endif
+#endif

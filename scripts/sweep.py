@@ -1,0 +1,75 @@
+#!/usr/bin/env python
+"""BASELINE configs[2]: fused selective scan (+gate) fwd and bwd over L x d_inner x dtype, CUDA-event timed (median of
+`--iters`, L2 flushed between iterations), reported as algorithmic GB/s and % of the measured HBM peak.
+Usage: python scripts/sweep.py [--B 16] [--out profiles/r01_sweep.md]"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from mmidet_b200 import ops  # noqa: E402
+
+
+def alg_bytes(B, L, ED, N, s):
+    return B * L * ED * s * 4 + B * L * N * s * 2 + (ED * N + ED) * 4, B * L * ED * s * 7 + B * L * N * s * 4 + 2 * (ED * N + ED) * 4
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--B", type=int, default=16)
+    ap.add_argument("--iters", type=int, default=7)
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    peak = 6538.0
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    dev, N = "cuda", 16
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timeit(fn):
+        for _ in range(2):
+            fn()
+        ts = []
+        for _ in range(a.iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2]
+
+    lines = [f"| dtype | B | L | d_inner | fwd ms | fwd GB/s | bwd ms | bwd GB/s | fwd+bwd GB/s | % of {peak:.0f} GB/s |", "|---|---|---|---|---|---|---|---|---|---|"]
+    for dname, dt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+        for L in (400, 1600, 6400, 25600):
+            for ED in (256, 512, 1024):
+                B = a.B if L * ED <= 6400 * 1024 else max(2, a.B // 4)
+                torch.manual_seed(0)
+                x = torch.randn(B, L, ED, device=dev).to(dt)
+                delta = torch.nn.functional.softplus(torch.randn(B, L, ED, device=dev) - 3).to(dt)
+                z = torch.randn(B, L, ED, device=dev).to(dt)
+                Bm, Cm = torch.randn(2, B, L, N, device=dev).to(dt)
+                dout = torch.randn(B, L, ED, device=dev).to(dt)
+                D = torch.ones(ED, device=dev)
+                A = -torch.arange(1, N + 1, device=dev, dtype=torch.float32).repeat(ED, 1)
+                fb, bb = alg_bytes(B, L, ED, N, x.element_size())
+                tf = timeit(lambda: ops.selscan_fwd_raw(x, delta, A, Bm, Cm, D, z=z, want_chk=True))
+                _, _, chk, saved = ops.selscan_fwd_raw(x, delta, A, Bm, Cm, D, z=z, want_chk=True)
+                tb = timeit(lambda: ops.selscan_bwd_raw(saved, chk, dout))
+                tot = (fb + bb) / (tf + tb) / 1e6
+                lines.append(f"| {dname} | {B} | {L} | {ED} | {tf:.3f} | {fb/tf/1e6:.0f} | {tb:.3f} | {bb/tb/1e6:.0f} | {tot:.0f} | {100*tot/peak:.1f} |")
+                print(lines[-1], flush=True)
+                del x, delta, z, Bm, Cm, dout, chk, saved
+    if a.out:
+        with open(a.out, "w") as f:
+            f.write("# Fused selective scan sweep (BASELINE configs[2]), one B200, S4D-real A, gate fused, checkpoints written\n\n")
+            f.write("\n".join(lines) + "\n")
+
+
+if __name__ == "__main__":
+    main()
