@@ -107,6 +107,21 @@ void mmi_ffm_kept_range(int H, int W, int *r0, int *r1, int *c0, int *c1);
 int mmi_separation_loss(const float *M, float *loss, int l, int K, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Depthwise causal conv1d (+ bias) + SiLU on channels-last tokens.  Replaces the x-branch prologue of
+ * MambaBlock.forward (models/mamba.py:176-180): transpose -> nn.Conv1d(ED, ED, K, groups=ED, padding=K-1)[..., :L]
+ * -> transpose -> F.silu, without the transposes:
+ *     y[t, d] = act(bias[d] + sum_{j<K} w[d, j] * x[t - (K-1) + j, d]),   x[t<0] = 0,   act = SiLU if silu else identity.
+ *   x, y, dy, dx : (B, L, ED) dtype with row pitches in elements (x may be the first half of in_proj's output);
+ *   w (ED, K) fp32 contiguous (= conv1d.weight (ED, 1, K), models/mamba.py:125); bias (ED) fp32, nullable; K in 1..4.
+ * The backward overwrites dx, dw (ED, K) fp32 and dbias (ED) fp32 (nullable); dw / dbias are summed with fp32 atomics.
+ * --------------------------------------------------------------------------------------------------------- */
+int mmi_causal_conv1d_fwd(const void *x, const float *w, const float *bias, void *y, int B, int L, int ED, int K, int64_t x_ld,
+                          int64_t y_ld, int dtype, int silu, void *stream);
+int mmi_causal_conv1d_bwd(const void *x, const float *w, const float *bias, const void *dy, void *dx, float *dw, float *dbias,
+                          int B, int L, int ED, int K, int64_t x_ld, int64_t dy_ld, int64_t dx_ld, int dtype, int silu,
+                          void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Host-buffer entry (end-to-end path used by bench.py `e2e`): same maths as mmi_selscan_fwd followed by
  * mmi_selscan_bwd, with every pointer a HOST pointer (pinned memory recommended).  Copies inputs H2D, runs
  * forward + backward on an internal stream, copies out/dx/ddelta/dz/dB/dC/dA/dD back and synchronises.

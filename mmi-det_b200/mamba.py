@@ -8,8 +8,8 @@ module; the library is loaded lazily by the operator layer):
     MambaBlock       models/mamba.py:117-353   ResidualBlock  models/mamba.py:89-115      Mamba   models/mamba.py:56-87
 
 What differs is only where the arithmetic runs: `MambaBlock.selective_scan` and the SiLU gate (models/mamba.py:212-233,
-184-186) go through the fused sm_100a kernels (ops.selective_scan); the four projections stay nn.Linear (cuBLAS), the
-depthwise causal conv stays nn.Conv1d (cuDNN), as the north_star prescribes.  Unlike the reference the block is
+184-186) go through the fused sm_100a kernels (ops.selective_scan); the four projections stay nn.Linear (cuBLAS); the
+depthwise causal conv + SiLU prologue (models/mamba.py:176-180) runs as one channels-last kernel.  Unlike the reference the block is
 half/bf16-clean: inputs of any float dtype are accepted and the input dtype is returned.
 
 `MambaFusion` is the cross-modal block the north_star names (the reference ships none): it keeps the I/O
@@ -109,7 +109,11 @@ class MambaBlock(nn.Module):
         L = x.shape[1]
         xz = self.in_proj(x)
         xs, z = xz.chunk(2, dim=-1)  # views of one GEMM output: passed to the kernel by row pitch, never copied
-        xs = F.silu(self.conv1d(xs.transpose(1, 2))[:, :, :L].transpose(1, 2))
+        if self.config.d_conv <= 4 and self.conv1d.groups == self.conv1d.in_channels:
+            # depthwise causal conv + SiLU on the channels-last tokens (no transposes, models/mamba.py:176-180)
+            xs = ops.causal_conv1d_silu(xs, self.conv1d.weight, self.conv1d.bias)
+        else:  # kernel sizes the fused kernel does not cover: stock cuDNN path
+            xs = F.silu(self.conv1d(xs.transpose(1, 2))[:, :, :L].transpose(1, 2))
         y = self.ssm(xs, z=z)  # = ssm(x) * silu(z): the gate of models/mamba.py:184-186 is fused into the scan
         return self.out_proj(y.to(xz.dtype))
 

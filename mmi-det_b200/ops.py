@@ -119,3 +119,49 @@ def selective_scan(x, delta, A, B, C, D, z=None, flags: int = 0):
     """Fused selective scan. Shapes as models/mamba.py:212-220: x, delta (B, L, ED); A (ED, N); B, C (B, L, N);
     D (ED).  Returns y (B, L, ED) = hs @ C + D * x, times silu(z) when `z` (B, L, ED) is given."""
     return _SelectiveScan.apply(x, delta, A, B, C, D, z, flags)
+
+
+class _CausalConv1dSiLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, silu):
+        global launches
+        lib = _lib.load()
+        _require_cuda(x, "causal_conv1d")
+        Bsz, L, ED = x.shape
+        K = weight.shape[-1]
+        x = _rows(x)
+        w = weight.detach().reshape(ED, K).float().contiguous()
+        b = None if bias is None else bias.detach().float().contiguous()
+        y = torch.empty((Bsz, L, ED), dtype=x.dtype, device=x.device)
+        _lib.check(lib.mmi_causal_conv1d_fwd(_ptr(x), _ptr(w), _ptr(b), _ptr(y), Bsz, L, ED, K, x.stride(1), y.stride(1),
+                                             _DT[x.dtype], int(silu), _stream(x)), "mmi_causal_conv1d_fwd")
+        launches += 1
+        ctx.save_for_backward(x, w, *([b] if b is not None else []))
+        ctx.silu, ctx.wshape, ctx.wdtype, ctx.bdtype = silu, weight.shape, weight.dtype, None if bias is None else bias.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        global launches
+        lib = _lib.load()
+        x, w, *rest = ctx.saved_tensors
+        b = rest[0] if rest else None
+        Bsz, L, ED = x.shape
+        K = w.shape[1]
+        dy = _rows(dy.to(x.dtype))
+        dx = torch.empty((Bsz, L, ED), dtype=x.dtype, device=x.device)
+        dw = torch.empty_like(w)
+        db = torch.empty(ED, dtype=torch.float32, device=x.device) if b is not None else None
+        _lib.check(lib.mmi_causal_conv1d_bwd(_ptr(x), _ptr(w), _ptr(b), _ptr(dy), _ptr(dx), _ptr(dw), _ptr(db), Bsz, L, ED, K,
+                                             x.stride(1), dy.stride(1), dx.stride(1), _DT[x.dtype], int(ctx.silu), _stream(x)),
+                   "mmi_causal_conv1d_bwd")
+        launches += 1
+        return dx, dw.reshape(ctx.wshape).to(ctx.wdtype), (None if db is None else db.to(ctx.bdtype)), None
+
+
+def causal_conv1d_silu(x, weight, bias=None, silu: bool = True):
+    """Depthwise causal conv1d + SiLU on (B, L, ED) tokens: the x-branch prologue of MambaBlock.forward
+    (models/mamba.py:176-180) without the transposes.  weight (ED, 1, K) as nn.Conv1d stores it, bias (ED) or None."""
+    if x.dtype not in _DT:
+        x = x.float()
+    return _CausalConv1dSiLU.apply(x, weight, bias, silu)

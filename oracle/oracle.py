@@ -357,3 +357,42 @@ def separation_loss(M):
         for j in range(i + 1, l):
             acc += float(M[i] @ M[j])
     return acc / (l * (l - 1))
+
+
+# ----------------------------------------------------------------------------------------------
+# depthwise causal conv1d + SiLU on channels-last tokens (models/mamba.py:176-180 with nn.Conv1d of :125-128)
+def causal_conv1d_silu(x, w, bias=None, silu=True, dtype=np.float64):
+    """x (B, L, ED); w (ED, K) [= conv1d.weight[:, 0, :]]; pre[t] = bias + sum_j w[:, j] * x[t-(K-1)+j]; y = silu(pre)."""
+    x = np.asarray(x, dtype)
+    w = np.asarray(w, dtype)
+    Bsz, L, ED = x.shape
+    K = w.shape[1]
+    xp = np.concatenate([np.zeros((Bsz, K - 1, ED), dtype), x], axis=1)
+    pre = np.zeros((Bsz, L, ED), dtype) + (0 if bias is None else np.asarray(bias, dtype))
+    for j in range(K):
+        pre = pre + w[:, j] * xp[:, j:j + L]
+    return pre / (1 + np.exp(-pre)) if silu else pre
+
+
+def causal_conv1d_silu_bwd(x, w, bias, dy, silu=True, dtype=np.float64):
+    """-> dx (B, L, ED), dw (ED, K), dbias (ED): adjoint of causal_conv1d_silu."""
+    x = np.asarray(x, dtype)
+    w = np.asarray(w, dtype)
+    dy = np.asarray(dy, dtype)
+    Bsz, L, ED = x.shape
+    K = w.shape[1]
+    xp = np.concatenate([np.zeros((Bsz, K - 1, ED), dtype), x], axis=1)
+    pre = np.zeros((Bsz, L, ED), dtype) + (0 if bias is None else np.asarray(bias, dtype))
+    for j in range(K):
+        pre = pre + w[:, j] * xp[:, j:j + L]
+    if silu:
+        s = 1 / (1 + np.exp(-pre))
+        dpre = dy * s * (1 + pre * (1 - s))
+    else:
+        dpre = dy
+    dxp = np.zeros_like(xp)
+    dw = np.zeros_like(w)
+    for j in range(K):
+        dxp[:, j:j + L] += w[:, j] * dpre
+        dw[:, j] = (dpre * xp[:, j:j + L]).sum((0, 1))
+    return dxp[:, K - 1:], dw, dpre.sum((0, 1))

@@ -101,3 +101,29 @@ def test_module_deepcopy_and_pickle():
     c = pickle.loads(pickle.dumps(fus))(x)
     for u, v, w in zip(a, b, c):
         assert torch.equal(u, v) and torch.equal(u, w)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("shape,K", [((2, 70, 40), 4), ((1, 3, 8), 4), ((3, 129, 136), 3), ((2, 257, 512), 4), ((1, 33, 16), 2)])
+def test_causal_conv1d_silu_vs_oracle(shape, K, dtype, tol):
+    """channels-last depthwise causal conv + SiLU, forward and all three gradients, incl. a strided (chunk view) input,
+    segment-boundary lengths (33, 129, 257 = kConvSeg multiples + 1) and ED not a multiple of the 128-channel block."""
+    from mmidet_b200 import ops
+    from oracle import oracle as O
+    B, L, ED = shape
+    rng = np.random.default_rng(L + ED)
+    xz = torch.from_numpy(rng.standard_normal((B, L, 2 * ED)).astype(np.float32)).cuda().to(dtype).requires_grad_(True)
+    w = torch.from_numpy((rng.standard_normal((ED, 1, K)) * 0.5).astype(np.float32)).cuda().requires_grad_(True)
+    b = torch.from_numpy(rng.standard_normal(ED).astype(np.float32)).cuda().requires_grad_(True)
+    g = torch.from_numpy(rng.standard_normal((B, L, ED)).astype(np.float32)).cuda().to(dtype)
+    x = xz.chunk(2, dim=-1)[0]  # row pitch 2*ED, as in MambaBlock.forward
+    y = ops.causal_conv1d_silu(x, w, b)
+    gxz, gw, gb = torch.autograd.grad(y, [xz, w, b], g)
+    xn = x.detach().float().cpu().numpy()
+    yr = O.causal_conv1d_silu(xn, w.detach().cpu().numpy()[:, 0, :], b.detach().cpu().numpy())
+    dx, dw, db = O.causal_conv1d_silu_bwd(xn, w.detach().cpu().numpy()[:, 0, :], b.detach().cpu().numpy(), g.float().cpu().numpy())
+    assert relerr(y.detach().float().cpu().numpy(), yr) <= tol
+    assert relerr(gxz[..., :ED].float().cpu().numpy(), dx) <= tol
+    assert float(gxz[..., ED:].abs().max()) == 0.0
+    assert relerr(gw.cpu().numpy()[:, 0, :], dw) <= max(tol, 2e-5)
+    assert relerr(gb.cpu().numpy(), db) <= max(tol, 2e-5)

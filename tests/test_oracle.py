@@ -108,3 +108,23 @@ def test_ffm_matches_reference(golden, tag):
 def test_separation_loss_matches_reference(golden):
     g = golden("seploss")
     assert abs(O.separation_loss(g["M"]) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+
+
+def test_causal_conv_oracle_matches_torch_conv1d():
+    """the oracle's conv restatement vs the exact torch ops of models/mamba.py:176-180 (Conv1d padding=K-1, [:L], silu)."""
+    import torch
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    for K in (4, 2):
+        B, L, ED = 2, 19, 8
+        conv = torch.nn.Conv1d(ED, ED, kernel_size=K, groups=ED, padding=K - 1).double()
+        x = torch.randn(B, L, ED, dtype=torch.float64, requires_grad=True)
+        y = F.silu(conv(x.transpose(1, 2))[:, :, :L].transpose(1, 2))
+        g = torch.randn_like(y)
+        gx, gw, gb = torch.autograd.grad(y, [x, conv.weight, conv.bias], g)
+        w = conv.weight.detach().numpy()[:, 0, :]
+        b = conv.bias.detach().numpy()
+        assert np.allclose(O.causal_conv1d_silu(x.detach().numpy(), w, b), y.detach().numpy(), atol=1e-12)
+        dx, dw, db = O.causal_conv1d_silu_bwd(x.detach().numpy(), w, b, g.numpy())
+        assert np.allclose(dx, gx.numpy(), atol=1e-12) and np.allclose(dw, gw.numpy()[:, 0, :], atol=1e-12)
+        assert np.allclose(db, gb.numpy(), atol=1e-12)
