@@ -34,7 +34,9 @@ enum { MMI_OK = 0, MMI_ERR_ARG = 1, MMI_ERR_CUDA = 2, MMI_ERR_UNSUPPORTED = 3 };
 enum {
     MMI_FLAG_NO_GEOM = 1,      /* disable the geometric-A fast path (A[d,n] == (n+1)*A[d,0], the S4D-real init) */
     MMI_FLAG_CFG_SHIFT = 4,    /* bits 4..7: pick a CTA shape (channel warps x time warps x stages) for tuning runs; */
-    MMI_FLAG_CFG_MASK = 0xF0   /*            0 = default.  Results do not depend on it.                                */
+    MMI_FLAG_CFG_MASK = 0xF0,  /*            0 = default.  Results do not depend on it.                                */
+    MMI_FLAG_NSEG_SHIFT = 8,   /* bits 8..15: force the number of L segments of the forward (1..32); 0 = heuristic */
+    MMI_FLAG_NSEG_MASK = 0xFF00
 };
 
 const char *mmi_last_error(void);
@@ -53,12 +55,17 @@ int mmi_device_info(int *sm_count, int *cc_major, int *cc_minor);
  *   chk  (nullable) : (B, ceil(L/chunk), ED, N) fp32; chk[b,j] = state entering step j*chunk.  Written for the
  *                     backward pass, which recomputes states chunk by chunk instead of materialising (B,L,ED,N).
  *   chunk           : checkpoint interval, must equal mmi_selscan_chunk() when chk != NULL
+ *   ws   (nullable) : device workspace of mmi_selscan_fwd_ws_bytes() bytes.  With it, when B * ED alone cannot fill the
+ *                     GPU (small batches, inference), L is cut into segments scanned by different CTAs of the same
+ *                     launch: every segment first publishes (end state from zero, sum of delta), later segments chain
+ *                     those summaries (decoupled look-back) and then scan for real.  Without it one CTA walks all of L.
  *   N must be 16 (the reference default d_state, models/mamba.py:35).
  * --------------------------------------------------------------------------------------------------------- */
 int mmi_selscan_chunk(void);
+int64_t mmi_selscan_fwd_ws_bytes(int B, int L, int ED, int N);
 int mmi_selscan_fwd(const void *x, const void *delta, const void *z, const float *A, const void *Bm, const void *Cm,
-                    const float *D, const float *h0, void *out, float *hT, float *chk, int B, int L, int ED, int N,
-                    int64_t x_ld, int64_t delta_ld, int64_t z_ld, int64_t out_ld, int chunk, int dtype, int flags,
+                    const float *D, const float *h0, void *out, float *hT, float *chk, void *ws, int B, int L, int ED,
+                    int N, int64_t x_ld, int64_t delta_ld, int64_t z_ld, int64_t out_ld, int chunk, int dtype, int flags,
                     void *stream);
 
 /* Backward of the above.  Replaces autograd through models/mamba.py:222-231 and PScan.backward

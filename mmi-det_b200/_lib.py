@@ -19,6 +19,7 @@ NVCC_FLAGS = ["-t", "8", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-
 MMI_F32, MMI_BF16, MMI_F16 = 0, 1, 2
 FLAG_NO_GEOM = 1
 FLAG_CFG_SHIFT = 4
+FLAG_NSEG_SHIFT = 8
 
 _lib = None
 
@@ -58,7 +59,8 @@ _SIGNATURES = {
     "mmi_version": (_i, []),
     "mmi_device_info": (_i, [_c.POINTER(_i)] * 3),
     "mmi_selscan_chunk": (_i, []),
-    "mmi_selscan_fwd": (_i, [_vp] * 11 + [_i] * 4 + [_i64] * 4 + [_i] * 3 + [_vp]),
+    "mmi_selscan_fwd_ws_bytes": (_i64, [_i] * 4),
+    "mmi_selscan_fwd": (_i, [_vp] * 12 + [_i] * 4 + [_i64] * 4 + [_i] * 3 + [_vp]),
     "mmi_selscan_bwd_ws_bytes": (_i64, [_i] * 4),
     "mmi_selscan_bwd": (_i, [_vp] * 17 + [_i] * 4 + [_i64] * 4 + [_i] * 3 + [_vp]),
     "mmi_pscan_ws_bytes": (_i64, [_i] * 4),

@@ -110,14 +110,20 @@ int mmi_device_info(int *sms, int *maj, int *min) {
 
 int mmi_selscan_chunk(void) { return kChunk; }
 
+int64_t mmi_selscan_fwd_ws_bytes(int B, int L, int ED, int N) {
+    (void)L; (void)N;
+    if (B <= 0 || ED <= 0) return 0;
+    return selscan_fwd_ws_bytes(B, ED);
+}
+
 int mmi_selscan_fwd(const void *x, const void *delta, const void *z, const float *A, const void *Bm, const void *Cm,
-                    const float *D, const float *h0, void *out, float *hT, float *chk, int B, int L, int ED, int N,
-                    int64_t x_ld, int64_t delta_ld, int64_t z_ld, int64_t out_ld, int chunk, int dtype, int flags,
+                    const float *D, const float *h0, void *out, float *hT, float *chk, void *ws, int B, int L, int ED,
+                    int N, int64_t x_ld, int64_t delta_ld, int64_t z_ld, int64_t out_ld, int chunk, int dtype, int flags,
                     void *stream) {
     if (!x || !delta || !A || !Bm || !Cm || !D || !out) { set_error("mmi_selscan_fwd: null required pointer"); return MMI_ERR_ARG; }
-    const void *ptrs[] = {x, delta, z, out, Bm, Cm, chk, hT, h0};
-    const int64_t lds[] = {x_ld, delta_ld, z ? z_ld : 0, out_ld, 0, 0, 0, 0, 0};
-    if (int e = check_scan_args("mmi_selscan_fwd", B, L, ED, N, dtype, ptrs, lds, 9)) return e;
+    const void *ptrs[] = {x, delta, z, out, Bm, Cm, chk, hT, h0, ws};
+    const int64_t lds[] = {x_ld, delta_ld, z ? z_ld : 0, out_ld, 0, 0, 0, 0, 0, 0};
+    if (int e = check_scan_args("mmi_selscan_fwd", B, L, ED, N, dtype, ptrs, lds, 10)) return e;
     if (chk && chunk != kChunk) { set_error("mmi_selscan_fwd: chunk=%d, expected mmi_selscan_chunk()=%d", chunk, kChunk); return MMI_ERR_ARG; }
     if (int e = require_device()) return e;
     FwdParams p{};
@@ -126,7 +132,7 @@ int mmi_selscan_fwd(const void *x, const void *delta, const void *z, const float
     p.B = B; p.L = L; p.ED = ED;
     p.x_ld = x_ld; p.d_ld = delta_ld; p.z_ld = z_ld; p.o_ld = out_ld;
     p.flags = flags;
-    return selscan_fwd_launch(p, dtype, static_cast<cudaStream_t>(stream));
+    return selscan_fwd_launch(p, dtype, ws, static_cast<cudaStream_t>(stream));
 }
 
 int64_t mmi_selscan_bwd_ws_bytes(int B, int L, int ED, int N) {

@@ -132,7 +132,7 @@ int mmi_selscan_fwd_bwd_host(const void *x, const void *delta, const void *z, co
         // stage 2: forward + backward
         MMI_CK(cudaStreamWaitEvent(s_comp, g_hws.in_done[sl], 0), "cudaStreamWaitEvent");
         if (int e = mmi_selscan_fwd(d_x, d_d, z ? d_z : nullptr, (const float *)d_A, d_B, d_C, (const float *)d_D, nullptr, d_o,
-                                    nullptr, (float *)d_chk, nb, L, ED, N, ED, ED, ED, ED, kChunk, dtype, flags, s_comp))
+                                    nullptr, (float *)d_chk, nullptr, nb, L, ED, N, ED, ED, ED, ED, kChunk, dtype, flags, s_comp))
             return e;
         if (int e = mmi_selscan_bwd(d_x, d_d, z ? d_z : nullptr, (const float *)d_A, d_B, d_C, (const float *)d_D, d_g,
                                     (const float *)d_chk, d_dx, d_dd, z ? d_dz : nullptr, d_dA, d_dB, d_dC, d_dD, d_ws, nb, L,

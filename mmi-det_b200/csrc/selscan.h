@@ -16,6 +16,10 @@ struct FwdParams {
     int B, L, ED;
     int64_t x_ld, d_ld, z_ld, o_ld;
     int flags;
+    // L split over CTAs (filled by the launcher): segment s covers super-tiles [s*seg_tiles, (s+1)*seg_tiles)
+    int nseg, seg_tiles, ntile_c;
+    unsigned *seg_ticket, *seg_flags;  // start-order ticket; per (b, segment, channel tile) publication counters
+    float *seg_ws;                     // (B, nseg, ED, N + 1): end state of the segment from zero | sum of delta
 };
 
 struct BwdParams {
@@ -31,7 +35,8 @@ struct BwdParams {
     int flags;
 };
 
-int selscan_fwd_launch(const FwdParams &p, int dtype, cudaStream_t st);
+int selscan_fwd_launch(const FwdParams &p, int dtype, void *ws, cudaStream_t st);
+int64_t selscan_fwd_ws_bytes(int B, int ED);
 int selscan_bwd_launch(BwdParams p, int dtype, void *ws, cudaStream_t st);
 int64_t selscan_bwd_ws_bytes(int B, int L, int ED);
 int sm_count();

@@ -25,6 +25,7 @@
 // exp() is MUFU ex2 on delta*A*log2(e); when a channel's A row is geometric, A[d,n] = (n+1) A[d,0] (the S4D-real init
 // of models/mamba.py:158-159, which the reference training loop never updates), a[t,n] = r^(n+1) needs
 // one ex2 per step instead of N (detected on the device, per CTA; MMI_FLAG_NO_GEOM forces the general path).
+#include <algorithm>
 #include <cstring>
 #include <type_traits>
 
@@ -85,9 +86,10 @@ __device__ __forceinline__ void load16(const float *p, float2 (&v)[8]) {  // 16 
     }
 }
 
-template <typename T, int WC, int WT, int STAGES, int TCH, bool GEOM, bool HAS_Z>
+template <typename T, int WC, int WT, int STAGES, int TCH, bool SPLIT, bool GEOM, bool HAS_Z>
 __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, unsigned char *smem, const float2 (&A2p)[8],
-                                         float A2base, float Dd, int c0, int b, int wc, int wt, int lane, int c, bool active) {
+                                         float A2base, float Dd, int c0, int b, int seg, int ctile, int wc, int wt, int lane, int c,
+                                         bool active) {
     using Lay = FwdLayout<T, WC, WT, STAGES, TCH>;
     static_assert(TCH % kBlk == 0, "chunks are scanned in blocks of kBlk steps");
     constexpr int N = kN, TC = Lay::TC, ST = Lay::ST, CH = Lay::CH, NW = Lay::NW;
@@ -99,38 +101,79 @@ __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, 
     float *bc32 = reinterpret_cast<float *>(smem + Lay::BC32_OFF) + warp * 2 * TC * N;
 
     const int L = p.L, ED = p.ED;
-    const int ntiles = (L + ST - 1) / ST, nchk = (L + kChunk - 1) / kChunk;
+    const int ntiles_all = (L + ST - 1) / ST, nchk = (L + kChunk - 1) / kChunk;
+    const int tile_lo = seg * p.seg_tiles, ntiles = min(p.seg_tiles, ntiles_all - tile_lo);  // this CTA's segment of L
     const int cl = wc * 32 + lane, tb = wt * TC;
 
-    auto issue = [&](int s, int ti) {  // one elected thread: the 5 tile loads of a super-tile arrive on full[s]
+    // one elected thread: the tile loads of a super-tile arrive on full[s] (the summary pass needs x, delta and B only)
+    auto issue = [&](int s, int ti, bool full_pass) {
         unsigned char *st = smem + size_t(s) * Lay::STAGE_BYTES;
-        const uint32_t total = uint32_t(Lay::TILE_BYTES) * (HAS_Z ? 3u : 2u) + 2u * uint32_t(Lay::BCT_BYTES);
+        const uint32_t total = full_pass ? uint32_t(Lay::TILE_BYTES) * (HAS_Z ? 3u : 2u) + 2u * uint32_t(Lay::BCT_BYTES)
+                                         : uint32_t(Lay::TILE_BYTES) * 2u + uint32_t(Lay::BCT_BYTES);
         mbar_arrive_expect_tx(&full[s], total);
         tma_load_3d(st, &tm.x, c0, ti * ST, b, &full[s]);
         tma_load_3d(st + Lay::TILE_BYTES, &tm.d, c0, ti * ST, b, &full[s]);
-        if (HAS_Z) tma_load_3d(st + 2 * Lay::TILE_BYTES, &tm.z, c0, ti * ST, b, &full[s]);
+        if (HAS_Z && full_pass) tma_load_3d(st + 2 * Lay::TILE_BYTES, &tm.z, c0, ti * ST, b, &full[s]);
         tma_load_3d(st + 3 * Lay::TILE_BYTES, &tm.B, 0, ti * ST, b, &full[s]);
-        tma_load_3d(st + 3 * Lay::TILE_BYTES + Lay::BCT_BYTES, &tm.C, 0, ti * ST, b, &full[s]);
+        if (full_pass) tma_load_3d(st + 3 * Lay::TILE_BYTES + Lay::BCT_BYTES, &tm.C, 0, ti * ST, b, &full[s]);
     };
 
-    // initial carry = h0 (reference: zeros, models/mamba.py:252)
-    if (wt == 0) {
-        const float4 *h0 = (p.h0 && active) ? reinterpret_cast<const float4 *>(p.h0 + (int64_t(b) * ED + c) * N) : nullptr;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) carry[k * 32] = h0 ? h0[k] : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    if (threadIdx.x == 0)
-        for (int s = 0; s < STAGES && s < ntiles; ++s) issue(s, s);
-    float2 hlast[8];  // state after the newest super-tile (kept by the last time-warp, for hT)
+    float2 hlast[8];  // state after the newest super-tile (kept by the last time-warp: segment summary, carry, hT)
 #pragma unroll
     for (int k = 0; k < 8; ++k) hlast[k] = make_float2(0.f, 0.f);
+    float sdseg = 0.f;  // sum of delta over the segment so far (summary pass, last time-warp)
+    int g = 0;          // super-tiles processed so far over both passes: stage / mbarrier-parity / carry-buffer bookkeeping
 
-    for (int it = 0; it < ntiles; ++it) {
-        const int s = it % STAGES, t0 = it * ST;
+    // When L is split over several CTAs (p.nseg > 1), every CTA but the one owning the last segment first reduces its
+    // segment to (end state from zero, sum of delta) -- pass 0: sweep A + fold only, no C / z loads, no output -- and
+    // publishes it; pass 1 then waits for the summaries of the earlier segments (decoupled look-back through global
+    // memory), chains them onto h0 and scans the segment for real.
+    for (int pass = (SPLIT && seg < p.nseg - 1) ? 0 : 1; pass < 2; ++pass) {
+    const bool full_pass = !SPLIT || pass == 1;
+    if (SPLIT && full_pass && seg > 0) {  // look-back: wait until every earlier segment of this (batch, channel tile) is published
+        if (threadIdx.x == 0) {
+            for (int sp = 0; sp < seg; ++sp) {
+                const volatile unsigned *f = p.seg_flags + (int64_t(b) * p.nseg + sp) * p.ntile_c + ctile;
+                const long long tw = clock64();
+                while (*f < unsigned(WC)) {
+                    if (clock64() - tw > 20000000000LL) __trap();  // ~10 s: a lost predecessor traps instead of hanging
+                }
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+    if (wt == 0) {  // entry state of the pass: zeros (summary) | h0 (reference: zeros, models/mamba.py:252) chained through
+        float2 hin[8];  //                                         the earlier segments' summaries
+        const float4 *h0 = (full_pass && p.h0 && active) ? reinterpret_cast<const float4 *>(p.h0 + (int64_t(b) * ED + c) * N) : nullptr;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float4 w = h0 ? h0[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+            hin[2 * k] = make_float2(w.x, w.y);
+            hin[2 * k + 1] = make_float2(w.z, w.w);
+        }
+        if (SPLIT && full_pass && active) {
+            for (int sp = 0; sp < seg; ++sp) {
+                const float *sw = p.seg_ws + ((int64_t(b) * p.nseg + sp) * ED + c) * (N + 1);
+                float2 a2[8];
+                decay16<GEOM>(__ldcg(sw + N), A2base, A2p, a2);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) hin[k] = fma2(a2[k], hin[k], make_float2(__ldcg(sw + 2 * k), __ldcg(sw + 2 * k + 1)));
+            }
+        }
+        float4 *cin = carry + (g & 1) * WC * 4 * 32;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cin[k * 32] = make_float4(hin[2 * k].x, hin[2 * k].y, hin[2 * k + 1].x, hin[2 * k + 1].y);
+    }
+    if (threadIdx.x == 0)
+        for (int i = 0; i < STAGES && i < ntiles; ++i) issue((g + i) % STAGES, tile_lo + i, full_pass);
+
+    for (int it = 0; it < ntiles; ++it, ++g) {
+        const int s = g % STAGES, t0 = (tile_lo + it) * ST;
         unsigned char *st = smem + size_t(s) * Lay::STAGE_BYTES;
         const T *sx = reinterpret_cast<const T *>(st) + tb * CH + cl, *sd = sx + ST * CH, *sz = sd + ST * CH;
         T *so = const_cast<T *>(sz);
-        mbar_wait(&full[s], (it / STAGES) & 1);
+        mbar_wait(&full[s], (g / STAGES) & 1);
 
         const float *fB, *fC;
         if constexpr (sizeof(T) == 2) {  // widen this chunk's B / C rows once per warp instead of once per use
@@ -138,7 +181,7 @@ __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, 
             const T *gC = reinterpret_cast<const T *>(st + 3 * Lay::TILE_BYTES + Lay::BCT_BYTES) + tb * N;
             for (int i = lane; i < TC * N; i += 32) {
                 bc32[i] = to_f32<T>(gB[i]);
-                bc32[TC * N + i] = to_f32<T>(gC[i]);
+                if (full_pass) bc32[TC * N + i] = to_f32<T>(gC[i]);
             }
             __syncwarp();
             fB = bc32;
@@ -187,13 +230,50 @@ __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, 
         // the previous super-tile's output store has had a whole sweep to drain; its stage can be refilled
         if (threadIdx.x == 0 && it >= 1 && it - 1 + STAGES < ntiles) {
             bulk_wait_read<0>();
-            issue((it - 1) % STAGES, it - 1 + STAGES);
+            issue((g - 1) % STAGES, tile_lo + it - 1 + STAGES, full_pass);
+        }
+        if (SPLIT && !full_pass) {  // summary pass: only the running end state of the segment is needed
+            if (wt == WT - 1) {
+                float2 hs[8];
+                const float4 *cin = carry + (g & 1) * WC * 4 * 32;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float4 w = cin[k * 32];
+                    hs[2 * k] = make_float2(w.x, w.y);
+                    hs[2 * k + 1] = make_float2(w.z, w.w);
+                }
+#pragma unroll
+                for (int v = 0; v < WT - 1; ++v) {
+                    float2 a2[8];
+                    const float sv = sumD[(v * WC + wc) * 32 + lane];
+                    sdseg += sv;
+                    decay16<GEOM>(sv, A2base, A2p, a2);
+                    const float4 *e = reinterpret_cast<const float4 *>(smem + Lay::SUM_OFF) + (v * WC + wc) * 4 * 32 + lane;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float4 w = e[k * 32];
+                        hs[2 * k] = fma2(a2[2 * k], hs[2 * k], make_float2(w.x, w.y));
+                        hs[2 * k + 1] = fma2(a2[2 * k + 1], hs[2 * k + 1], make_float2(w.z, w.w));
+                    }
+                }
+                float2 a2[8];
+                decay16<GEOM>(S, A2base, A2p, a2);
+                sdseg += S;
+                float4 *cout = carry + ((g + 1) & 1) * WC * 4 * 32;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) hlast[k] = fma2(a2[k], hs[k], acc[k]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    cout[k * 32] = make_float4(hlast[2 * k].x, hlast[2 * k].y, hlast[2 * k + 1].x, hlast[2 * k + 1].y);
+            }
+            __syncthreads();  // summaries and stage s are free again
+            continue;
         }
 
         // ---- fold: state entering this warp's chunk ---------------------------------------------------------
         float2 h2[8];
         {
-            const float4 *cin = carry + (it & 1) * WC * 4 * 32;
+            const float4 *cin = carry + (g & 1) * WC * 4 * 32;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const float4 w = cin[k * 32];
@@ -218,7 +298,7 @@ __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, 
         if (wt == WT - 1) {  // carry for the next super-tile = this chunk's entry state pushed through its own summary
             float2 a2[8];
             decay16<GEOM>(S, A2base, A2p, a2);
-            float4 *cout = carry + ((it + 1) & 1) * WC * 4 * 32;
+            float4 *cout = carry + ((g + 1) & 1) * WC * 4 * 32;
 #pragma unroll
             for (int k = 0; k < 8; ++k) hlast[k] = fma2(a2[k], h2[k], acc[k]);
 #pragma unroll
@@ -278,9 +358,26 @@ __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, 
             bulk_commit();
         }
     }
+    if (SPLIT && !full_pass) {  // publish the segment summary, then raise the flag the later segments spin on
+        if (wt == WT - 1) {
+            if (active) {
+                float *sw = p.seg_ws + ((int64_t(b) * p.nseg + seg) * ED + c) * (N + 1);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    __stcg(sw + 2 * k, hlast[k].x);
+                    __stcg(sw + 2 * k + 1, hlast[k].y);
+                }
+                __stcg(sw + N, sdseg);
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicAdd(p.seg_flags + (int64_t(b) * p.nseg + seg) * p.ntile_c + ctile, 1u);
+        }
+    }
+    }  // pass
     if (threadIdx.x == 0) bulk_wait_read<0>();  // shared memory must outlive the last tile store's reads
 
-    if (p.hT && active && wt == WT - 1) {  // steps past L are identities (zero-filled delta), so this is h[L-1]
+    if (p.hT && active && wt == WT - 1 && seg == p.nseg - 1) {  // steps past L are identities (zero-filled delta), so this is h[L-1]
         float *hT = p.hT + (int64_t(b) * ED + c) * N;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -290,7 +387,7 @@ __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, 
     }
 }
 
-template <typename T, int WC, int WT, int STAGES, int TCH>
+template <typename T, int WC, int WT, int STAGES, int TCH, bool SPLIT>
 __global__ void __launch_bounds__(WC *WT * 32) selscan_fwd_kernel(const FwdParams p, const __grid_constant__ FwdMaps tm) {
     using Lay = FwdLayout<T, WC, WT, STAGES, TCH>;
     constexpr int N = kN, CH = Lay::CH;
@@ -299,7 +396,17 @@ __global__ void __launch_bounds__(WC *WT * 32) selscan_fwd_kernel(const FwdParam
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wc = warp % WC, wt = warp / WC;
-    const int b = blockIdx.y, c0 = blockIdx.x * CH;
+    int b = blockIdx.y, ctile = blockIdx.x, seg = 0;
+    if constexpr (SPLIT) {  // L split over CTAs: take a ticket so that segments start in dependency order (earlier ones first)
+        __shared__ unsigned ticket;
+        if (tid == 0) ticket = atomicAdd(p.seg_ticket, 1u);
+        __syncthreads();
+        const int v = int(ticket);
+        ctile = v % p.ntile_c;
+        b = (v / p.ntile_c) % p.B;
+        seg = v / (p.ntile_c * p.B);
+    }
+    const int c0 = ctile * CH;
     const int c = c0 + wc * 32 + lane;
     const bool active = c < p.ED;
 
@@ -323,7 +430,8 @@ __global__ void __launch_bounds__(WC *WT * 32) selscan_fwd_kernel(const FwdParam
     const bool geom = __syncthreads_and(ok);  // also publishes the mbarrier inits
     const bool has_z = p.z != nullptr;
 
-#define MMI_FWD_BODY(G, Z) fwd_body<T, WC, WT, STAGES, TCH, G, Z>(p, tm, smem, A2p, A2base, Dd, c0, b, wc, wt, lane, c, active)
+#define MMI_FWD_BODY(G, Z) \
+    fwd_body<T, WC, WT, STAGES, TCH, SPLIT, G, Z>(p, tm, smem, A2p, A2base, Dd, c0, b, seg, ctile, wc, wt, lane, c, active)
     if (geom) {
         if (has_z) MMI_FWD_BODY(true, true);
         else MMI_FWD_BODY(true, false);
@@ -334,10 +442,19 @@ __global__ void __launch_bounds__(WC *WT * 32) selscan_fwd_kernel(const FwdParam
 #undef MMI_FWD_BODY
 }
 
+constexpr int kMaxSeg = 32;  // upper bound on the number of L segments (sizes the workspace)
+
+// workspace of the L split: [ticket | flags (B, nseg, ntile_c)] [summaries (B, nseg, ED, N + 1) fp32]
+static size_t seg_header_bytes(int B, int ntile_c) { return (size_t(16) + size_t(B) * kMaxSeg * ntile_c * 4 + 255) & ~size_t(255); }
+int64_t selscan_fwd_ws_bytes(int B, int ED) {
+    return int64_t(seg_header_bytes(B, (ED + 31) / 32)) + int64_t(B) * kMaxSeg * ED * (kN + 1) * 4;
+}
+
 template <typename T, int WC, int WT, int STAGES, int TCH = kFwdChunk>
-static int launch_fwd_t(const FwdParams &p, int dtype, cudaStream_t st) {
+static int launch_fwd_t(FwdParams p, int dtype, void *ws, cudaStream_t st) {
     using Lay = FwdLayout<T, WC, WT, STAGES, TCH>;
-    auto kern = selscan_fwd_kernel<T, WC, WT, STAGES, TCH>;
+    auto kern = selscan_fwd_kernel<T, WC, WT, STAGES, TCH, false>;
+    auto kern_split = selscan_fwd_kernel<T, WC, WT, STAGES, TCH, true>;
     FwdMaps tm;
     memset(&tm, 0, sizeof(tm));
     const uint64_t nb = p.B, L = p.L;
@@ -355,24 +472,48 @@ static int launch_fwd_t(const FwdParams &p, int dtype, cudaStream_t st) {
         if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Lay::SMEM)),
                                "selscan_fwd smem attribute"))
             return e;
+        if (int e = check_cuda(cudaFuncSetAttribute(kern_split, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Lay::SMEM)),
+                               "selscan_fwd smem attribute"))
+            return e;
         attr_dev = dev;
     }
-    const unsigned gx = (p.ED + Lay::CH - 1) / Lay::CH;
-    kern<<<dim3(gx, p.B), Lay::NW * 32, Lay::SMEM, st>>>(p, tm);
+    const int gx = (p.ED + Lay::CH - 1) / Lay::CH, ntiles = (p.L + Lay::ST - 1) / Lay::ST;
+    // L split: when B * (ED / CH) CTAs cannot fill the GPU (small batches, inference), cut L into segments scanned by
+    // different CTAs; each segment costs one extra summary pass over x / delta / B, so only split when SMs would idle
+    int nseg = 1;
+    if (ws) {
+        const int forced = (p.flags & MMI_FLAG_NSEG_MASK) >> MMI_FLAG_NSEG_SHIFT;
+        const int ctas = gx * p.B, slots = 2 * sm_count();
+        nseg = forced ? forced : (ctas * 2 <= slots ? slots / ctas : 1);
+        nseg = std::max(1, std::min({nseg, kMaxSeg, forced ? ntiles : ntiles / 2}));
+    }
+    p.seg_tiles = (ntiles + nseg - 1) / nseg;
+    p.nseg = (ntiles + p.seg_tiles - 1) / p.seg_tiles;
+    p.ntile_c = gx;
+    if (p.nseg > 1) {
+        const size_t hdr = seg_header_bytes(p.B, gx);
+        p.seg_ticket = static_cast<unsigned *>(ws);
+        p.seg_flags = p.seg_ticket + 4;
+        p.seg_ws = reinterpret_cast<float *>(static_cast<char *>(ws) + hdr);
+        if (int e = check_cuda(cudaMemsetAsync(ws, 0, hdr, st), "selscan_fwd segment flags memset")) return e;
+        kern_split<<<dim3(unsigned(gx) * p.B * p.nseg), Lay::NW * 32, Lay::SMEM, st>>>(p, tm);
+    } else {
+        kern<<<dim3(gx, p.B), Lay::NW * 32, Lay::SMEM, st>>>(p, tm);
+    }
     return check_cuda(cudaGetLastError(), "selscan_fwd launch");
 }
 
-int selscan_fwd_launch(const FwdParams &p, int dtype, cudaStream_t st) {
+int selscan_fwd_launch(const FwdParams &p, int dtype, void *ws, cudaStream_t st) {
     const int cfg = (p.flags & MMI_FLAG_CFG_MASK) >> MMI_FLAG_CFG_SHIFT;
 #define MMI_FWD_DISPATCH(T)                                        \
     switch (cfg) {                                                 \
-        case 1: return launch_fwd_t<T, 2, 4, 3>(p, dtype, st);     \
-        case 2: return launch_fwd_t<T, 1, 8, 2>(p, dtype, st);     \
-        case 3: return launch_fwd_t<T, 1, 2, 4>(p, dtype, st);     \
-        case 4: return launch_fwd_t<T, 1, 8, 3, 8>(p, dtype, st);  \
-        case 5: return launch_fwd_t<T, 1, 8, 4, 8>(p, dtype, st);  \
-        case 6: return launch_fwd_t<T, 2, 8, 2, 8>(p, dtype, st);  \
-        default: return launch_fwd_t<T, 1, 4, 3>(p, dtype, st);    \
+        case 1: return launch_fwd_t<T, 2, 4, 3>(p, dtype, ws, st);     \
+        case 2: return launch_fwd_t<T, 1, 8, 2>(p, dtype, ws, st);     \
+        case 3: return launch_fwd_t<T, 1, 2, 4>(p, dtype, ws, st);     \
+        case 4: return launch_fwd_t<T, 1, 8, 3, 8>(p, dtype, ws, st);  \
+        case 5: return launch_fwd_t<T, 1, 8, 4, 8>(p, dtype, ws, st);  \
+        case 6: return launch_fwd_t<T, 2, 8, 2, 8>(p, dtype, ws, st);  \
+        default: return launch_fwd_t<T, 1, 4, 3>(p, dtype, ws, st);    \
     }
     switch (dtype) {
         case MMI_F32: MMI_FWD_DISPATCH(float)

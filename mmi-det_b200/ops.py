@@ -61,8 +61,9 @@ def selscan_fwd_raw(x, delta, A, Bm, Cm, D, z=None, h0=None, want_state=False, w
     chunk = lib.mmi_selscan_chunk()
     chk = torch.empty((Bsz, (L + chunk - 1) // chunk, ED, N), dtype=torch.float32, device=x.device) if want_chk else None
     h0 = None if h0 is None else h0.float().contiguous()
+    ws = torch.empty(lib.mmi_selscan_fwd_ws_bytes(Bsz, L, ED, N), dtype=torch.uint8, device=x.device)  # L-split summaries
     _lib.check(lib.mmi_selscan_fwd(_ptr(x), _ptr(delta), _ptr(z), _ptr(A), _ptr(Bm), _ptr(Cm), _ptr(D), _ptr(h0),
-                                   _ptr(out), _ptr(hT), _ptr(chk), Bsz, L, ED, N, x.stride(1), delta.stride(1),
+                                   _ptr(out), _ptr(hT), _ptr(chk), _ptr(ws), Bsz, L, ED, N, x.stride(1), delta.stride(1),
                                    z.stride(1) if z is not None else 0, out.stride(1), chunk, _DT[dt], flags,
                                    _stream(x)), "mmi_selscan_fwd")
     launches += 1

@@ -36,14 +36,14 @@ def test_version_and_chunk(lib):
 
 def test_argument_errors_are_reported(lib):
     null = ctypes.c_void_p(None)
-    rc = lib.mmi_selscan_fwd(null, null, null, null, null, null, null, null, null, null, null, 1, 8, 16, 16, 16, 16,
+    rc = lib.mmi_selscan_fwd(null, null, null, null, null, null, null, null, null, null, null, null, 1, 8, 16, 16, 16, 16,
                              16, 16, 16, 0, 0, null)
     assert rc != 0 and b"null" in lib.mmi_last_error()
     one = ctypes.c_void_p(256)  # never dereferenced: validation fails first
-    rc = lib.mmi_selscan_fwd(one, one, null, one, one, one, one, null, one, null, null, 1, 8, 12, 16, 12, 12, 0, 12, 16,
+    rc = lib.mmi_selscan_fwd(one, one, null, one, one, one, one, null, one, null, null, null, 1, 8, 12, 16, 12, 12, 0, 12, 16,
                              0, 0, null)
     assert rc != 0 and b"multiple of 8" in lib.mmi_last_error()
-    rc = lib.mmi_selscan_fwd(one, one, null, one, one, one, one, null, one, null, null, 1, 8, 16, 8, 16, 16, 0, 16, 16,
+    rc = lib.mmi_selscan_fwd(one, one, null, one, one, one, one, null, one, null, null, null, 1, 8, 16, 8, 16, 16, 0, 16, 16,
                              0, 0, null)
     assert rc != 0 and b"d_state" in lib.mmi_last_error()
 

@@ -100,6 +100,28 @@ def test_cta_shapes_agree(cfg, random_A):
         assert relerr(v.cpu().numpy(), u.cpu().numpy()) <= 2e-5
 
 
+@pytest.mark.parametrize("nseg", [2, 5, 32])
+@pytest.mark.parametrize("cfg", [0, 1])
+@pytest.mark.parametrize("random_A", [False, True])
+def test_l_split_across_ctas(nseg, cfg, random_A):
+    """L cut into segments scanned by different CTAs of one launch (segment summaries published through global memory,
+    decoupled look-back): same outputs, final state and checkpoints as one CTA walking all of L; h0 != 0, ragged tail,
+    more segments requested than super-tiles exist."""
+    from mmidet_b200 import ops
+    B, L, ED = 2, 715, 72
+    inp = scan_inputs(B, L, ED, seed=nseg, random_A=random_A)
+    a = {k: _t(v) for k, v in inp.items()}
+    h0 = torch.randn(B, ED, 16, device="cuda")
+    run = lambda fl: ops.selscan_fwd_raw(a["x"], a["delta"], a["A"], a["Bm"], a["Cm"], a["D"], z=a["z"], h0=h0,
+                                         want_state=True, want_chk=True, flags=fl)
+    o1, hT1, chk1, _ = run((cfg << 4) | (1 << 8))
+    o2, hT2, chk2, _ = run((cfg << 4) | (nseg << 8))
+    for u, v in ((o1, o2), (hT1, hT2), (chk1, chk2)):
+        assert relerr(v.cpu().numpy(), u.cpu().numpy()) <= 2e-5
+    res = _run(inp, flags=(cfg << 4) | (nseg << 8))
+    _compare(res, _oracle(inp), TOL32)
+
+
 def test_no_gate():
     inp = scan_inputs(2, 50, 32, seed=3, random_A=True)
     res = _run(inp, gate=False)
