@@ -33,6 +33,10 @@ struct BwdParams {
     int ntile_c;   // channel tiles per row (grid.x)
     int64_t x_ld, d_ld, z_ld, g_ld;
     int flags;
+    // L split over CTAs (filled by the launcher), as in FwdParams
+    int nseg, seg_tiles;
+    unsigned *seg_ticket, *seg_flags;
+    float *seg_ws;  // (B, nseg, ED, N + 1): a*g leaving the segment when nothing enters it | sum of delta
 };
 
 int selscan_fwd_launch(const FwdParams &p, int dtype, void *ws, cudaStream_t st);

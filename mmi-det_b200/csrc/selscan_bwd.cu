@@ -28,6 +28,7 @@
 //       products g*delta*x are reduced the same way -> dB partial.
 // Per-CTA dB/dC partials and per-batch dA/dD partials go to a workspace; selscan_bwd_finish_kernel reduces them
 // deterministically (no atomics).
+#include <algorithm>
 #include <cstring>
 
 #include "../../include/mmidet_b200.h"
@@ -128,10 +129,10 @@ template <> __device__ __forceinline__ void st_pair<__half>(__half *p, float2 v)
 }
 __device__ __forceinline__ float pick(float2 v, int j) { return j ? v.y : v.x; }
 
-template <typename T, int WT, int STAGES, bool GEOM, bool HAS_Z>
+template <typename T, int WT, int STAGES, bool SPLIT, bool GEOM, bool HAS_Z>
 __device__ __forceinline__ void bwd_body(const BwdParams &p, const BwdMaps &tm, unsigned char *smem, uint32_t tmem_base,
                                          const float2 (&A2p)[2][8], const float (&A2base)[2], const float (&Dd)[2], int c0,
-                                         int b, int wt, int lane, int c, const bool (&active)[2]) {
+                                         int b, int seg, int ctile, int wt, int lane, int c, const bool (&active)[2]) {
     using Lay = BwdLayout<T, WT, STAGES>;
     constexpr int N = kN, TC = Lay::TC, ST = Lay::ST, CH = Lay::CH, NW = Lay::NW;
     constexpr float kLn2 = 0.6931471805599453f;
@@ -145,32 +146,32 @@ __device__ __forceinline__ void bwd_body(const BwdParams &p, const BwdMaps &tm, 
     const uint32_t tslot = tmem_base + (uint32_t(wt & 3) * 32u << 16) + uint32_t(wt >> 2) * (2 * TC * N);
 
     const int L = p.L, ED = p.ED;
-    const int ntiles = (L + ST - 1) / ST, nchk = (L + TC - 1) / TC;
+    const int ntiles_all = (L + ST - 1) / ST, nchk = (L + TC - 1) / TC;
+    const int tile_lo = seg * p.seg_tiles, ntiles = min(p.seg_tiles, ntiles_all - tile_lo);  // this CTA's segment of L
     const int tb = wt * TC, cl = 2 * lane;
     const int64_t row_b = int64_t(b) * L;
 
-    auto issue = [&](int s, int tj) {  // one elected thread: the 6 tile loads of super-tile tj arrive on full[s]
+    // one elected thread: the tile loads of super-tile tj arrive on full[s] (the summary pass needs delta, dout, z, C only)
+    auto issue = [&](int s, int tj, bool full_pass) {
         unsigned char *st = smem + size_t(s) * Lay::STAGE_BYTES;
-        const uint32_t total = uint32_t(Lay::TILE_BYTES) * (HAS_Z ? 4u : 3u) + 2u * uint32_t(Lay::BCT_BYTES);
+        const uint32_t total = uint32_t(Lay::TILE_BYTES) * ((HAS_Z ? 3u : 2u) + (full_pass ? 1u : 0u)) +
+                               (full_pass ? 2u : 1u) * uint32_t(Lay::BCT_BYTES);
         mbar_arrive_expect_tx(&full[s], total);
-        tma_load_3d(st, &tm.x, c0, tj * ST, b, &full[s]);
+        if (full_pass) tma_load_3d(st, &tm.x, c0, tj * ST, b, &full[s]);
         tma_load_3d(st + Lay::TILE_BYTES, &tm.d, c0, tj * ST, b, &full[s]);
         tma_load_3d(st + 2 * Lay::TILE_BYTES, &tm.g, c0, tj * ST, b, &full[s]);
         if (HAS_Z) tma_load_3d(st + 3 * Lay::TILE_BYTES, &tm.z, c0, tj * ST, b, &full[s]);
-        tma_load_3d(st + 4 * Lay::TILE_BYTES, &tm.B, 0, tj * ST, b, &full[s]);
+        if (full_pass) tma_load_3d(st + 4 * Lay::TILE_BYTES, &tm.B, 0, tj * ST, b, &full[s]);
         tma_load_3d(st + 4 * Lay::TILE_BYTES + Lay::BCT_BYTES, &tm.C, 0, tj * ST, b, &full[s]);
     };
 
-    // zero the carried a*g (buffer 0) and the parked dA
-    if (wt == 0) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) carry[k * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    // zero the parked dA
 #pragma unroll
     for (int k = 0; k < 8; ++k) dApark[k * NW * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
     float dDacc[2] = {0.f, 0.f};
-    if (threadIdx.x == 0)
-        for (int s = 0; s < STAGES && s < ntiles; ++s) issue(s, ntiles - 1 - s);
+    float sdseg[2] = {0.f, 0.f};  // sum of delta over the segment so far (summary pass, warp 0)
+    float2 glast[2][8];           // a*g leaving the segment so far (summary pass, warp 0)
+    int g = 0;                    // super-tiles processed over both passes: stage / parity / carry-buffer bookkeeping
 
     // sum over the warp's 64 channels of the per-lane vectors parked in `scr` ([kRB][4][32] float4, one float4 per
     // (step, state quad, lane)); lane l sums 16 source lanes of item l & 15, halves combined by one shuffle.
@@ -192,13 +193,62 @@ __device__ __forceinline__ void bwd_body(const BwdParams &p, const BwdMaps &tm, 
         s1.y += __shfl_xor_sync(0xffffffffu, s1.y, 16);
         const int t = tblk + (item >> 2), k4 = item & 3;
         if (half == 0 && t < L)
-            __stcs(reinterpret_cast<float4 *>(p.ws_bc + ((row_b + t) * p.ntile_c + blockIdx.x) * (2 * N) + which * N + 4 * k4),
+            __stcs(reinterpret_cast<float4 *>(p.ws_bc + ((row_b + t) * p.ntile_c + ctile) * (2 * N) + which * N + 4 * k4),
                    make_float4(s0.x, s0.y, s1.x, s1.y));
         __syncwarp();
     };
 
-    for (int it = 0; it < ntiles; ++it) {
-        const int s = it % STAGES, tj = ntiles - 1 - it, t0 = tj * ST;
+    // When L is split over several CTAs (SPLIT), every CTA but the one owning the earliest segment first reduces its
+    // segment to (a*g leaving it when nothing enters, sum of delta) -- pass 0: sweep A + fold only -- and publishes it;
+    // pass 1 waits for the summaries of the LATER segments (decoupled look-back through global memory), chains them and
+    // then runs the segment for real.
+    for (int pass = (SPLIT && seg > 0) ? 0 : 1; pass < 2; ++pass) {
+    const bool full_pass = !SPLIT || pass == 1;
+    if (SPLIT && full_pass && seg < p.nseg - 1) {
+        if (threadIdx.x == 0) {
+            for (int sp = p.nseg - 1; sp > seg; --sp) {
+                const volatile unsigned *f = p.seg_flags + (int64_t(b) * p.nseg + sp) * p.ntile_c + ctile;
+                const long long tw = clock64();
+                while (*f == 0u) {
+                    if (clock64() - tw > 20000000000LL) __trap();  // ~10 s: a lost predecessor traps instead of hanging
+                }
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+    if (wt == 0) {  // a*g entering the segment: zero, or the later segments' summaries chained from the end of L
+        float2 gin[2][8];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) gin[j][k] = make_float2(0.f, 0.f);
+        if (SPLIT && full_pass) {
+            for (int sp = p.nseg - 1; sp > seg; --sp) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (!active[j]) continue;
+                    const float *sw = p.seg_ws + ((int64_t(b) * p.nseg + sp) * ED + c + j) * (N + 1);
+                    float2 a2[8];
+                    bdecay16<GEOM>(__ldcg(sw + N), A2base[j], A2p[j], a2);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        gin[j][k] = fma2(a2[k], gin[j][k], make_float2(__ldcg(sw + 2 * k), __ldcg(sw + 2 * k + 1)));
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                carry[(((g & 1) * 2 + j) * 4 + k) * 32] =
+                    make_float4(gin[j][2 * k].x, gin[j][2 * k].y, gin[j][2 * k + 1].x, gin[j][2 * k + 1].y);
+    }
+    if (threadIdx.x == 0)
+        for (int i = 0; i < STAGES && i < ntiles; ++i) issue((g + i) % STAGES, tile_lo + ntiles - 1 - i, full_pass);
+
+    for (int it = 0; it < ntiles; ++it, ++g) {
+        const int s = g % STAGES, tj = tile_lo + ntiles - 1 - it, t0 = tj * ST;
         unsigned char *st = smem + size_t(s) * Lay::STAGE_BYTES;
         T *sx = reinterpret_cast<T *>(st) + tb * CH + cl, *sd = sx + ST * CH, *sg = sd + ST * CH, *sz = sg + ST * CH;
         float *sdy, *se;  // fp32 dy and dz factor: in place over dout / z for fp32 I/O, separate arrays for 16-bit I/O
@@ -209,14 +259,14 @@ __device__ __forceinline__ void bwd_body(const BwdParams &p, const BwdMaps &tm, 
             sdy = reinterpret_cast<float *>(sg);
             se = reinterpret_cast<float *>(sz);
         }
-        mbar_wait(&full[s], (it / STAGES) & 1);
+        mbar_wait(&full[s], (g / STAGES) & 1);
 
         const float *fB, *fC;
         if constexpr (sizeof(T) == 2) {
             const T *gB = reinterpret_cast<const T *>(st + 4 * Lay::TILE_BYTES) + tb * N;
             const T *gC = reinterpret_cast<const T *>(st + 4 * Lay::TILE_BYTES + Lay::BCT_BYTES) + tb * N;
             for (int i = lane; i < TC * N; i += 32) {
-                bc32[i] = to_f32<T>(gB[i]);
+                if (full_pass) bc32[i] = to_f32<T>(gB[i]);
                 bc32[TC * N + i] = to_f32<T>(gC[i]);
             }
             __syncwarp();
@@ -230,7 +280,7 @@ __device__ __forceinline__ void bwd_body(const BwdParams &p, const BwdMaps &tm, 
         // chunk checkpoint (state entering step t0 + tb): issued now, consumed in P1
         float4 ckv[2][4];
         {
-            const bool inb = t0 + tb < L;
+            const bool inb = full_pass && t0 + tb < L;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const float4 *ck = reinterpret_cast<const float4 *>(
@@ -299,14 +349,14 @@ __device__ __forceinline__ void bwd_body(const BwdParams &p, const BwdMaps &tm, 
         // the previous super-tile's output stores have had a whole sweep to drain; its stage can be refilled
         if (threadIdx.x == 0 && it >= 1 && it - 1 + STAGES < ntiles) {
             bulk_wait_read<0>();
-            issue((it - 1) % STAGES, ntiles - 1 - (it - 1 + STAGES));
+            issue((g - 1) % STAGES, tile_lo + ntiles - 1 - (it - 1 + STAGES), full_pass);
         }
 
         // ---- fold: a*g entering this chunk from the later ones --------------------------------------------------
         float2 ga[2][8];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const float4 *cin = carry + ((it & 1) * 2 + j) * 4 * 32;
+            const float4 *cin = carry + ((g & 1) * 2 + j) * 4 * 32;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const float4 w = cin[k * 32];
@@ -318,6 +368,10 @@ __device__ __forceinline__ void bwd_body(const BwdParams &p, const BwdMaps &tm, 
         for (int v = WT - 1; v >= 1; --v) {
             if (v > wt) {
                 const float2 sdv = sumD[v * 32 + lane];
+                if (SPLIT && !full_pass) {
+                    sdseg[0] += sdv.x;
+                    sdseg[1] += sdv.y;
+                }
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     float2 a2[8];
@@ -336,14 +390,23 @@ __device__ __forceinline__ void bwd_body(const BwdParams &p, const BwdMaps &tm, 
             for (int j = 0; j < 2; ++j) {
                 float2 a2[8];
                 bdecay16<GEOM>(S[j], A2base[j], A2p[j], a2);
-                float4 *cout = carry + (((it + 1) & 1) * 2 + j) * 4 * 32;
+                float4 *cout = carry + (((g + 1) & 1) * 2 + j) * 4 * 32;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const float2 v0 = fma2(a2[2 * k], ga[j][2 * k], acc[j][2 * k]);
                     const float2 v1 = fma2(a2[2 * k + 1], ga[j][2 * k + 1], acc[j][2 * k + 1]);
                     cout[k * 32] = make_float4(v0.x, v0.y, v1.x, v1.y);
+                    if (SPLIT && !full_pass) {
+                        glast[j][2 * k] = v0;
+                        glast[j][2 * k + 1] = v1;
+                    }
                 }
+                if (SPLIT && !full_pass) sdseg[j] += S[j];
             }
+        }
+        if (SPLIT && !full_pass) {  // summary pass: nothing else to do for this super-tile
+            __syncthreads();        // summaries and stage s are free again
+            continue;
         }
 
         // ---- P1: recompute the chunk's states; park them in tensor memory; y -> dz; dC -------------------------
@@ -479,14 +542,31 @@ __device__ __forceinline__ void bwd_body(const BwdParams &p, const BwdMaps &tm, 
             bulk_commit();
         }
     }
+    if (SPLIT && !full_pass && wt == 0) {  // publish the segment summary, then raise the flag the earlier segments spin on
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (!active[j]) continue;
+            float *sw = p.seg_ws + ((int64_t(b) * p.nseg + seg) * ED + c + j) * (N + 1);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                __stcg(sw + 2 * k, glast[j][k].x);
+                __stcg(sw + 2 * k + 1, glast[j][k].y);
+            }
+            __stcg(sw + N, sdseg[j]);
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(p.seg_flags + (int64_t(b) * p.nseg + seg) * p.ntile_c + ctile, 1u);
+    }
+    }  // pass
     if (threadIdx.x == 0) bulk_wait_read<0>();
     __syncthreads();
 
-    // per-(batch, time-warp) partials of dA (A2 is A*log2e: dA = sum w delta, no rescale needed) and dD
+    // per-(batch, segment, time-warp) partials of dA (A2 is A*log2e: dA = sum w delta, no rescale needed) and dD
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
         if (active[j]) {
-            float *o = p.ws_ad + ((int64_t(b) * NW + wt) * ED + c + j) * (N + 1);
+            float *o = p.ws_ad + (((int64_t(b) * p.nseg + seg) * NW + wt) * ED + c + j) * (N + 1);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const float4 w = dApark[(j * 4 + k) * NW * 32];
@@ -500,7 +580,7 @@ __device__ __forceinline__ void bwd_body(const BwdParams &p, const BwdMaps &tm, 
     }
 }
 
-template <typename T, int WT, int STAGES>
+template <typename T, int WT, int STAGES, bool SPLIT>
 __global__ void __launch_bounds__(WT * 32, 1) selscan_bwd_kernel(const BwdParams p, const __grid_constant__ BwdMaps tm) {
     using Lay = BwdLayout<T, WT, STAGES>;
     constexpr int N = kN, CH = Lay::CH;
@@ -509,7 +589,17 @@ __global__ void __launch_bounds__(WT * 32, 1) selscan_bwd_kernel(const BwdParams
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Lay::BAR_OFF + STAGES * sizeof(uint64_t));
 
     const int tid = threadIdx.x, wt = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.y, c0 = blockIdx.x * CH;
+    int b = blockIdx.y, ctile = blockIdx.x, seg = 0;
+    if constexpr (SPLIT) {  // L split over CTAs: tickets hand out the LATER segments first (they are the predecessors)
+        __shared__ unsigned ticket;
+        if (tid == 0) ticket = atomicAdd(p.seg_ticket, 1u);
+        __syncthreads();
+        const int v = int(ticket);
+        ctile = v % p.ntile_c;
+        b = (v / p.ntile_c) % p.B;
+        seg = p.nseg - 1 - v / (p.ntile_c * p.B);
+    }
+    const int c0 = ctile * CH;
     const int c = c0 + 2 * lane;
     const bool active[2] = {c < p.ED, c + 1 < p.ED};
 
@@ -542,7 +632,8 @@ __global__ void __launch_bounds__(WT * 32, 1) selscan_bwd_kernel(const BwdParams
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     const bool has_z = p.z != nullptr;
-#define MMI_BWD_BODY(G, Z) bwd_body<T, WT, STAGES, G, Z>(p, tm, smem, tmem_base, A2p, A2base, Dd, c0, b, wt, lane, c, active)
+#define MMI_BWD_BODY(G, Z) \
+    bwd_body<T, WT, STAGES, SPLIT, G, Z>(p, tm, smem, tmem_base, A2p, A2base, Dd, c0, b, seg, ctile, wt, lane, c, active)
     if (geom) {
         if (has_z) MMI_BWD_BODY(true, true);
         else MMI_BWD_BODY(true, false);
@@ -583,12 +674,23 @@ __global__ void selscan_bwd_finish_kernel(const float *__restrict__ ws_bc, const
     }
 }
 
-constexpr int kBwdWT = 4;
+constexpr int kBwdWT = 4;  // time warps per CTA: their state history (2 channels x 16 states x 16 steps per lane) fills tensor memory
+constexpr int kBwdMaxSeg = 32;
+static size_t bwd_seg_header_bytes(int B, int ntile_c) { return (size_t(16) + size_t(B) * kBwdMaxSeg * ntile_c * 4 + 255) & ~size_t(255); }
+static size_t al256(size_t v) { return (v + 255) & ~size_t(255); }
+
+// workspace: [dB/dC partials (B, L, ntile_c, 2N)] [dA/dD partials (B, nseg, WT, ED, N+1)] [ticket | flags] [summaries]
+int64_t selscan_bwd_ws_bytes(int B, int L, int ED) {
+    const int64_t ntile = (ED + 63) / 64;
+    return int64_t(al256(size_t(B) * L * ntile * 2 * kN * 4)) + int64_t(al256(size_t(B) * kBwdMaxSeg * kBwdWT * ED * (kN + 1) * 4)) +
+           int64_t(bwd_seg_header_bytes(B, int(ntile))) + int64_t(B) * kBwdMaxSeg * ED * (kN + 1) * 4;
+}
 
 template <typename T> static int launch_bwd_t(BwdParams p, int dtype, void *ws, cudaStream_t st) {
     constexpr int WT = kBwdWT, STAGES = 2;
     using Lay = BwdLayout<T, WT, STAGES>;
-    auto kern = selscan_bwd_kernel<T, WT, STAGES>;
+    auto kern = selscan_bwd_kernel<T, WT, STAGES, false>;
+    auto kern_split = selscan_bwd_kernel<T, WT, STAGES, true>;
     static thread_local int attr_dev = -1;  // the opt-in is per device and sticky: set it once, not on every launch
     int dev = 0;
     cudaGetDevice(&dev);
@@ -596,12 +698,30 @@ template <typename T> static int launch_bwd_t(BwdParams p, int dtype, void *ws, 
         if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Lay::SMEM)),
                                "selscan_bwd smem attribute"))
             return e;
+        if (int e = check_cuda(cudaFuncSetAttribute(kern_split, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Lay::SMEM)),
+                               "selscan_bwd smem attribute"))
+            return e;
         attr_dev = dev;
     }
     const uint64_t rows = uint64_t(p.B) * p.L, nb = p.B, L = p.L;
     p.ntile_c = (p.ED + Lay::CH - 1) / Lay::CH;
-    p.ws_bc = static_cast<float *>(ws);
-    p.ws_ad = p.ws_bc + rows * p.ntile_c * 2 * kN;
+    const int ntiles = (p.L + Lay::ST - 1) / Lay::ST;
+    // L split (see the forward launcher): only when B * (ED / 64) CTAs leave SMs idle; one CTA per SM here
+    const int forced = (p.flags & MMI_FLAG_NSEG_MASK) >> MMI_FLAG_NSEG_SHIFT;
+    const int ctas = p.ntile_c * p.B, slots = sm_count();
+    int nseg = forced ? forced : (ctas * 2 <= slots ? slots / ctas : 1);
+    nseg = std::max(1, std::min({nseg, kBwdMaxSeg, forced ? ntiles : ntiles / 2}));
+    p.seg_tiles = (ntiles + nseg - 1) / nseg;
+    p.nseg = (ntiles + p.seg_tiles - 1) / p.seg_tiles;
+    char *w = static_cast<char *>(ws);
+    p.ws_bc = reinterpret_cast<float *>(w);
+    w += al256(size_t(rows) * p.ntile_c * 2 * kN * 4);
+    p.ws_ad = reinterpret_cast<float *>(w);
+    w += al256(size_t(p.B) * kBwdMaxSeg * WT * p.ED * (kN + 1) * 4);
+    p.seg_ticket = reinterpret_cast<unsigned *>(w);
+    p.seg_flags = p.seg_ticket + 4;
+    const size_t hdr = bwd_seg_header_bytes(p.B, p.ntile_c);
+    p.seg_ws = reinterpret_cast<float *>(w + hdr);
     BwdMaps tm;
     memset(&tm, 0, sizeof(tm));
     if (int e = make_tmap_3d(&tm.x, p.x, dtype, nb, L, p.ED, p.x_ld * sizeof(T), Lay::ST, Lay::CH)) return e;
@@ -615,18 +735,18 @@ template <typename T> static int launch_bwd_t(BwdParams p, int dtype, void *ws, 
     if (int e = make_tmap_3d(&tm.odd, p.ddelta, dtype, nb, L, p.ED, p.ED * sizeof(T), Lay::ST, Lay::CH)) return e;
     if (p.dz)
         if (int e = make_tmap_3d(&tm.odz, p.dz, dtype, nb, L, p.ED, p.ED * sizeof(T), Lay::ST, Lay::CH)) return e;
-    dim3 grid(p.ntile_c, p.B);
-    kern<<<grid, WT * 32, Lay::SMEM, st>>>(p, tm);
+    if (p.nseg > 1) {
+        if (int e = check_cuda(cudaMemsetAsync(p.seg_ticket, 0, hdr, st), "selscan_bwd segment flags memset")) return e;
+        kern_split<<<dim3(unsigned(p.ntile_c) * p.B * p.nseg), WT * 32, Lay::SMEM, st>>>(p, tm);
+    } else {
+        kern<<<dim3(p.ntile_c, p.B), WT * 32, Lay::SMEM, st>>>(p, tm);
+    }
     if (int e = check_cuda(cudaGetLastError(), "selscan_bwd launch")) return e;
     const int64_t work = int64_t(rows) * 2 * kN + int64_t(p.ED) * (kN + 1);
     selscan_bwd_finish_kernel<T><<<unsigned((work + 255) / 256), 256, 0, st>>>(
-        p.ws_bc, p.ws_ad, static_cast<T *>(p.dBm), static_cast<T *>(p.dCm), p.dA, p.dD, int64_t(rows), p.ntile_c, p.B * WT, p.ED);
+        p.ws_bc, p.ws_ad, static_cast<T *>(p.dBm), static_cast<T *>(p.dCm), p.dA, p.dD, int64_t(rows), p.ntile_c,
+        p.B * p.nseg * WT, p.ED);
     return check_cuda(cudaGetLastError(), "selscan_bwd finish launch");
-}
-
-int64_t selscan_bwd_ws_bytes(int B, int L, int ED) {
-    const int64_t ntile = (ED + 63) / 64;
-    return (int64_t(B) * L * ntile * 2 * kN + int64_t(B) * kBwdWT * ED * (kN + 1)) * 4;
 }
 
 int selscan_bwd_launch(BwdParams p, int dtype, void *ws, cudaStream_t st) {

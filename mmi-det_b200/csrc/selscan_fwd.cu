@@ -484,7 +484,7 @@ static int launch_fwd_t(FwdParams p, int dtype, void *ws, cudaStream_t st) {
     if (ws) {
         const int forced = (p.flags & MMI_FLAG_NSEG_MASK) >> MMI_FLAG_NSEG_SHIFT;
         const int ctas = gx * p.B, slots = 2 * sm_count();
-        nseg = forced ? forced : (ctas * 2 <= slots ? slots / ctas : 1);
+        nseg = forced ? forced : (ctas * 4 <= slots ? slots / ctas : 1);  // measured: splitting 128 CTAs in two loses
         nseg = std::max(1, std::min({nseg, kMaxSeg, forced ? ntiles : ntiles / 2}));
     }
     p.seg_tiles = (ntiles + nseg - 1) / nseg;
