@@ -180,13 +180,18 @@ __device__ __forceinline__ void bwd_body(const BwdParams &p, const BwdMaps &tm, 
         __syncwarp();
         const int item = lane & 15, half = lane >> 4;
         const float4 *src = scr + item * 32 + half * 16;
-        float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+        // four independent accumulator chains: the sum is latency-bound, not throughput-bound
+        float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f), u0 = make_float2(0.f, 0.f), u1 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float4 v = src[(i + lane) & 15];
+        for (int i = 0; i < 16; i += 2) {
+            const float4 v = src[(i + lane) & 15], w = src[(i + 1 + lane) & 15];
             s0 = add2(s0, make_float2(v.x, v.y));
             s1 = add2(s1, make_float2(v.z, v.w));
+            u0 = add2(u0, make_float2(w.x, w.y));
+            u1 = add2(u1, make_float2(w.z, w.w));
         }
+        s0 = add2(s0, u0);
+        s1 = add2(s1, u1);
         s0.x += __shfl_xor_sync(0xffffffffu, s0.x, 16);
         s0.y += __shfl_xor_sync(0xffffffffu, s0.y, 16);
         s1.x += __shfl_xor_sync(0xffffffffu, s1.x, 16);
