@@ -33,6 +33,8 @@ enum { MMI_OK = 0, MMI_ERR_ARG = 1, MMI_ERR_CUDA = 2, MMI_ERR_UNSUPPORTED = 3 };
 /* flags for the selective-scan entry points */
 enum {
     MMI_FLAG_NO_GEOM = 1,      /* disable the geometric-A fast path (A[d,n] == (n+1)*A[d,0], the S4D-real init) */
+    MMI_FLAG_DELTA_SOFTPLUS = 2, /* `delta` holds the pre-activation dt_proj(.) (models/mamba.py:203): the kernels apply softplus
+                                  on load and the backward returns the gradient w.r.t. the pre-activation */
     MMI_FLAG_CFG_SHIFT = 4,    /* bits 4..7: pick a CTA shape (channel warps x time warps x stages) for tuning runs; */
     MMI_FLAG_CFG_MASK = 0xF0,  /*            0 = default.  Results do not depend on it.                                */
     MMI_FLAG_NSEG_SHIFT = 8,   /* bits 8..15: force the number of L segments of the forward (1..32); 0 = heuristic */

@@ -18,6 +18,7 @@ NVCC_FLAGS = ["-t", "8", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-
 
 MMI_F32, MMI_BF16, MMI_F16 = 0, 1, 2
 FLAG_NO_GEOM = 1
+FLAG_DELTA_SOFTPLUS = 2
 FLAG_CFG_SHIFT = 4
 FLAG_NSEG_SHIFT = 8
 

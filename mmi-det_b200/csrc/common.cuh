@@ -38,6 +38,22 @@ __device__ __forceinline__ float rcp(float x) {  // MUFU.RCP
 }
 __device__ __forceinline__ float sigmoidf_fast(float z) { return rcp(1.0f + ex2(-kLog2e * z)); }
 
+__device__ __forceinline__ float lg2(float x) {  // MUFU.LG2
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// softplus with torch's semantics (F.softplus, beta = 1, threshold = 20; models/mamba.py:203): x above the threshold passes
+// through; log1p(e^x) is evaluated as a short series when e^x is small (lg2(1 + e) would lose it to rounding)
+__device__ __forceinline__ float softplus_fast(float x) {
+    const float e = ex2(kLog2e * x);
+    const float big = 0.6931471805599453f * lg2(1.0f + e);
+    const float small = e * fmaf(e, fmaf(e, 0.33333334f, -0.5f), 1.0f);
+    return x > 20.0f ? x : (e < 0.0078125f ? small : big);
+}
+// d softplus(x) / dx = sigmoid(x), recovered from s = softplus(x):  1 - e^(-s)
+__device__ __forceinline__ float softplus_grad_from_value(float s) { return 1.0f - ex2(-kLog2e * s); }
+
 // packed fp32x2 (FFMA2 / FMUL2 / FADD2 on sm_100): two lanes of work per issue slot
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }

@@ -295,6 +295,13 @@ __device__ __forceinline__ void bwd_body(const BwdParams &p, const BwdMaps &tm, 
             }
         }
 
+        if (p.flags & MMI_FLAG_DELTA_SOFTPLUS) {  // fused softplus(dt_proj(.)), models/mamba.py:203: activate this chunk's delta
+#pragma unroll                              // once, in place (sweep A, P1 and P3 all read the activated value)
+            for (int u = 0; u < TC; ++u) {
+                const float2 r = ld_pair<T>(sd + u * CH);
+                st_pair<T>(sd + u * CH, make_float2(softplus_fast(r.x), softplus_fast(r.y)));
+            }
+        }
         // ---- A: dy, dz factor, reverse-scan summary of the chunk ------------------------------------------------
         float2 acc[2][8];
         float S[2] = {0.f, 0.f};
@@ -522,6 +529,7 @@ __device__ __forceinline__ void bwd_body(const BwdParams &p, const BwdMaps &tm, 
                     const float gB = gBa.x + gBa.y;
                     odx[j] = fmaf(gB, dvj, Dd[j] * dyj);
                     odd[j] = fmaf(gB, xvj, dd);
+                    if (p.flags & MMI_FLAG_DELTA_SOFTPLUS) odd[j] *= softplus_grad_from_value(dvj);  // d/d(pre-activation)
                     dDacc[j] = fmaf(dyj, xvj, dDacc[j]);
                 }
                 st_pair<T>(sx + u * CH, make_float2(odx[0], odx[1]));  // dx, in place over x

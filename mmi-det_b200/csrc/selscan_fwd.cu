@@ -171,7 +171,8 @@ __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, 
     for (int it = 0; it < ntiles; ++it, ++g) {
         const int s = g % STAGES, t0 = (tile_lo + it) * ST;
         unsigned char *st = smem + size_t(s) * Lay::STAGE_BYTES;
-        const T *sx = reinterpret_cast<const T *>(st) + tb * CH + cl, *sd = sx + ST * CH, *sz = sd + ST * CH;
+        const T *sx = reinterpret_cast<const T *>(st) + tb * CH + cl, *sz = sx + 2 * ST * CH;
+        T *sd = const_cast<T *>(sx) + ST * CH;
         T *so = const_cast<T *>(sz);
         mbar_wait(&full[s], (g / STAGES) & 1);
 
@@ -191,6 +192,10 @@ __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, 
             fC = reinterpret_cast<const float *>(st + 3 * Lay::TILE_BYTES + Lay::BCT_BYTES) + tb * N;
         }
 
+        if (p.flags & MMI_FLAG_DELTA_SOFTPLUS) {  // fused softplus(dt_proj(.)), models/mamba.py:203: activate this chunk's delta
+#pragma unroll                              // once, in place, rounded to the I/O type exactly as the unfused path does
+            for (int u = 0; u < TC; ++u) sd[u * CH] = from_f32<T>(softplus_fast(to_f32<T>(sd[u * CH])));
+        }
         // ---- sweep A: chunk summary by direct evaluation (walk t backwards, S = sum of delta after t) ----------
         float2 acc[8];
 #pragma unroll

@@ -91,9 +91,10 @@ class MambaBlock(nn.Module):
         self.out_proj = nn.Linear(c.d_inner, c.d_model, bias=c.bias)
 
     # -- the hot path -----------------------------------------------------------------------------------------
-    def selective_scan(self, x, delta, A, B, C, D, z=None):
-        """models/mamba.py:212-233 (and :235-265, same maths) on the fused kernel; `z` additionally fuses the gate."""
-        return ops.selective_scan(x, delta, A, B, C, D, z=z)
+    def selective_scan(self, x, delta, A, B, C, D, z=None, delta_softplus=False):
+        """models/mamba.py:212-233 (and :235-265, same maths) on the fused kernel; `z` additionally fuses the gate,
+        `delta_softplus` the softplus of models/mamba.py:203."""
+        return ops.selective_scan(x, delta, A, B, C, D, z=z, delta_softplus=delta_softplus)
 
     selective_scan_seq = selective_scan
 
@@ -102,8 +103,8 @@ class MambaBlock(nn.Module):
         A = -torch.exp(self.A_log.float())
         dbc = self.x_proj(x)
         delta, B, C = torch.split(dbc, [c.dt_rank, c.d_state, c.d_state], dim=-1)
-        delta = F.softplus(self.dt_proj(delta))
-        return self.selective_scan(x, delta, A, B, C, self.D.float(), z=z)
+        # softplus(dt_proj(.)) of models/mamba.py:203 is applied inside the scan kernels (no elementwise pass, no cast)
+        return self.selective_scan(x, self.dt_proj(delta), A, B, C, self.D.float(), z=z, delta_softplus=True)
 
     def forward(self, x):
         L = x.shape[1]

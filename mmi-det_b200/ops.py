@@ -116,9 +116,13 @@ class _SelectiveScan(torch.autograd.Function):
         return cast(dx, 0), cast(dd, 1), cast(dA, 2), cast(dB, 3), cast(dC, 4), cast(dD, 5), (cast(dz, 6) if ctx.has_z else None), None
 
 
-def selective_scan(x, delta, A, B, C, D, z=None, flags: int = 0):
+def selective_scan(x, delta, A, B, C, D, z=None, flags: int = 0, delta_softplus: bool = False):
     """Fused selective scan. Shapes as models/mamba.py:212-220: x, delta (B, L, ED); A (ED, N); B, C (B, L, N);
-    D (ED).  Returns y (B, L, ED) = hs @ C + D * x, times silu(z) when `z` (B, L, ED) is given."""
+    D (ED).  Returns y (B, L, ED) = hs @ C + D * x, times silu(z) when `z` (B, L, ED) is given.
+    delta_softplus=True: `delta` is the pre-activation dt_proj(.) and softplus (models/mamba.py:203) is applied inside
+    the kernels (the returned gradient is then w.r.t. the pre-activation)."""
+    if delta_softplus:
+        flags |= _lib.FLAG_DELTA_SOFTPLUS
     return _SelectiveScan.apply(x, delta, A, B, C, D, z, flags)
 
 

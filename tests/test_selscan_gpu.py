@@ -122,6 +122,35 @@ def test_l_split_across_ctas(nseg, cfg, random_A):
     _compare(res, _oracle(inp), TOL32)
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, TOL32), (torch.bfloat16, TOL16)])
+@pytest.mark.parametrize("random_A", [False, True])
+def test_fused_softplus(dtype, tol, random_A):
+    """MMI_FLAG_DELTA_SOFTPLUS: delta passed as the pre-activation of models/mamba.py:203 (incl. values beyond torch's
+    threshold of 20 and very negative ones); outputs and all gradients (ddelta w.r.t. the pre-activation) vs the oracle
+    run on softplus(pre) with the chain rule applied on the host."""
+    from mmidet_b200 import ops
+    B, L, ED = 2, 150, 40
+    inp = scan_inputs(B, L, ED, seed=21, random_A=random_A)
+    rng = np.random.default_rng(5)
+    pre = (rng.standard_normal((B, L, ED)) * 2.0 - 3.0).astype(np.float32)
+    pre[0, 3, :4] = [25.0, 19.5, -30.0, -12.0]
+    cast = lambda a: torch.from_numpy(a).to(dtype).float().numpy()
+    pre_r = cast(pre)
+    sp = np.where(pre_r > 20, pre_r, np.log1p(np.exp(np.minimum(pre_r, 20)))).astype(np.float64)
+    rnd = {k: (cast(v) if k not in ("A", "D") else v) for k, v in inp.items()}
+    rnd["delta"] = cast(sp.astype(np.float32)).astype(np.float64) if dtype != torch.float32 else sp
+    ref = _oracle(rnd)
+    ref["ddelta"] = ref["ddelta"] * (1.0 / (1.0 + np.exp(-pre_r.astype(np.float64))))
+    leaves = {k: _t(rnd[k], torch.float32 if k in ("A", "D") else dtype).requires_grad_(True) for k in ("x", "z", "A", "Bm", "Cm", "D")}
+    tpre = _t(pre, dtype).requires_grad_(True)
+    out = ops.selective_scan(leaves["x"], tpre, leaves["A"], leaves["Bm"], leaves["Cm"], leaves["D"], z=leaves["z"], delta_softplus=True)
+    out.backward(_t(rnd["dout"], dtype))
+    res = {"out": out.detach().float().cpu().numpy(), "ddelta": tpre.grad.float().cpu().numpy()}
+    for k, n in dict(x="dx", z="dz", A="dA", Bm="dB", Cm="dC", D="dD").items():
+        res[n] = leaves[k].grad.float().cpu().numpy()
+    _compare(res, ref, tol)
+
+
 def test_no_gate():
     inp = scan_inputs(2, 50, 32, seed=3, random_A=True)
     res = _run(inp, gate=False)
