@@ -131,6 +131,16 @@ int mmi_causal_conv1d_bwd(const void *x, const float *w, const float *bias, cons
                           void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * RMSNorm over the last axis of (rows, C) tokens.  Replaces RMSNorm.forward (models/mamba.py:356-366):
+ *     y = x * rsqrt(mean(x^2, -1) + eps) * w          x, y, dy, dx : (rows, C) dtype with row pitches in elements; w (C) fp32
+ * The backward overwrites dx and dw (C) fp32 (summed with fp32 atomics).  C a multiple of 8, C <= 1024.
+ * --------------------------------------------------------------------------------------------------------- */
+int mmi_rmsnorm_fwd(const void *x, const float *w, void *y, int64_t rows, int C, int64_t x_ld, int64_t y_ld, float eps, int dtype,
+                    void *stream);
+int mmi_rmsnorm_bwd(const void *x, const float *w, const void *dy, void *dx, float *dw, int64_t rows, int C, int64_t x_ld,
+                    int64_t dy_ld, int64_t dx_ld, float eps, int dtype, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Host-buffer entry (end-to-end path used by bench.py `e2e`): same maths as mmi_selscan_fwd followed by
  * mmi_selscan_bwd, with every pointer a HOST pointer (pinned memory recommended).  Copies inputs H2D, runs
  * forward + backward on an internal stream, copies out/dx/ddelta/dz/dB/dC/dA/dD back and synchronises.

@@ -1,0 +1,220 @@
+// rmsnorm.cu -- RMSNorm over the channel axis of (rows, C) tokens, forward and backward, one warp per row.
+//
+// Replaces RMSNorm.forward (models/mamba.py:356-366): y = x * rsqrt(mean(x^2) + eps) * weight, which the reference (and
+// stock PyTorch) evaluates as five elementwise / reduction kernels per direction.  HBM-bound: the forward reads x and
+// writes y once (the row stays in registers between the reduction and the scaling); the backward reads x and dy once,
+//     dx = r * (w*dy - x * r^2 * mean(w*dy*x)),   r = rsqrt(mean(x^2) + eps),   dw = sum_rows dy * x * r,
+// with dw accumulated per warp over a strip of rows and finished with one fp32 atomic per (warp, channel).
+#include "../../include/mmidet_b200.h"
+#include "common.cuh"
+
+namespace mmi {
+
+constexpr int kRmsMaxC = 1024;           // channels per row held in registers (32 lanes x 4 x 8 float4 groups)
+constexpr int kRmsRowsPerWarp = 16;       // rows per warp strip in the backward (dw is reduced over the strip first)
+
+template <typename T> __device__ __forceinline__ void rms_load4(const T *p, float (&v)[4]);
+template <> __device__ __forceinline__ void rms_load4<float>(const float *p, float (&v)[4]) {
+    const float4 q = __ldg(reinterpret_cast<const float4 *>(p));
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+}
+template <> __device__ __forceinline__ void rms_load4<__nv_bfloat16>(const __nv_bfloat16 *p, float (&v)[4]) {
+    const uint2 q = __ldg(reinterpret_cast<const uint2 *>(p));
+    v[0] = __uint_as_float(q.x << 16); v[1] = __uint_as_float(q.x & 0xffff0000u);
+    v[2] = __uint_as_float(q.y << 16); v[3] = __uint_as_float(q.y & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void rms_load4<__half>(const __half *p, float (&v)[4]) {
+    const uint2 q = __ldg(reinterpret_cast<const uint2 *>(p));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&q.x)), b = __half22float2(*reinterpret_cast<const __half2 *>(&q.y));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+template <typename T> __device__ __forceinline__ void rms_store4(T *p, const float (&v)[4]);
+template <> __device__ __forceinline__ void rms_store4<float>(float *p, const float (&v)[4]) {
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void rms_store4<__nv_bfloat16>(__nv_bfloat16 *p, const float (&v)[4]) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 q;
+    q.x = *reinterpret_cast<const uint32_t *>(&a);
+    q.y = *reinterpret_cast<const uint32_t *>(&b);
+    *reinterpret_cast<uint2 *>(p) = q;
+}
+template <> __device__ __forceinline__ void rms_store4<__half>(__half *p, const float (&v)[4]) {
+    const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+    uint2 q;
+    q.x = *reinterpret_cast<const uint32_t *>(&a);
+    q.y = *reinterpret_cast<const uint32_t *>(&b);
+    *reinterpret_cast<uint2 *>(p) = q;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
+
+// NV = number of float4 groups per lane actually used (C <= 128 * NV); rows = B * L, x/y row pitches in elements
+template <typename T, int NV>
+__global__ void __launch_bounds__(128) rmsnorm_fwd_kernel(const T *__restrict__ x, const float *__restrict__ w, T *__restrict__ y,
+                                                          float *__restrict__ rstd, int64_t rows, int C, int64_t x_ld, int64_t y_ld,
+                                                          float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = int64_t(blockIdx.x) * 4 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float v[NV][4];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < C) {
+            rms_load4<T>(x + row * x_ld + c, v[i]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ss = fmaf(v[i][k], v[i][k], ss);
+        }
+    }
+    const float r = rsqrtf(warp_sum(ss) / float(C) + eps);
+    if (rstd && lane == 0) rstd[row] = r;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < C) {
+            const float4 ww = __ldg(reinterpret_cast<const float4 *>(w + c));
+            float o[4] = {v[i][0] * r * ww.x, v[i][1] * r * ww.y, v[i][2] * r * ww.z, v[i][3] * r * ww.w};
+            rms_store4<T>(y + row * y_ld + c, o);
+        }
+    }
+}
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(128) rmsnorm_bwd_kernel(const T *__restrict__ x, const float *__restrict__ w, const T *__restrict__ dy,
+                                                          T *__restrict__ dx, float *__restrict__ dw, int64_t rows, int C, int64_t x_ld,
+                                                          int64_t dy_ld, int64_t dx_ld, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row0 = (int64_t(blockIdx.x) * 4 + (threadIdx.x >> 5)) * kRmsRowsPerWarp;
+    float wv[NV][4], dwa[NV][4];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dwa[i][k] = 0.f;
+        if (c < C) {
+            const float4 ww = __ldg(reinterpret_cast<const float4 *>(w + c));
+            wv[i][0] = ww.x; wv[i][1] = ww.y; wv[i][2] = ww.z; wv[i][3] = ww.w;
+        }
+    }
+    for (int rr = 0; rr < kRmsRowsPerWarp; ++rr) {
+        const int64_t row = row0 + rr;
+        if (row >= rows) break;
+        float xv[NV][4], gv[NV][4];
+        float ss = 0.f, sg = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < C) {
+                rms_load4<T>(x + row * x_ld + c, xv[i]);
+                rms_load4<T>(dy + row * dy_ld + c, gv[i]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    ss = fmaf(xv[i][k], xv[i][k], ss);
+                    sg = fmaf(gv[i][k] * wv[i][k], xv[i][k], sg);
+                }
+            }
+        }
+        ss = warp_sum(ss);
+        sg = warp_sum(sg);
+        const float r = rsqrtf(ss / float(C) + eps);
+        const float coef = r * r * r * sg / float(C);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < C) {
+                float o[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    o[k] = fmaf(gv[i][k] * wv[i][k], r, -xv[i][k] * coef);
+                    dwa[i][k] = fmaf(gv[i][k] * r, xv[i][k], dwa[i][k]);
+                }
+                rms_store4<T>(dx + row * dx_ld + c, o);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < C && row0 < rows) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) atomicAdd(dw + c + k, dwa[i][k]);
+        }
+    }
+}
+
+template <typename T> static int rms_launch_t(bool bwd, const void *x, const float *w, const void *dy, void *out, float *dw, int64_t rows,
+                                              int C, int64_t x_ld, int64_t dy_ld, int64_t out_ld, float eps, cudaStream_t st) {
+    const T *xp = static_cast<const T *>(x);
+    const T *gp = static_cast<const T *>(dy);
+    T *op = static_cast<T *>(out);
+    if (bwd)
+        if (int e = check_cuda(cudaMemsetAsync(dw, 0, size_t(C) * 4, st), "rmsnorm dw memset")) return e;
+    const unsigned gf = unsigned((rows + 3) / 4), gb = unsigned((rows + 4 * kRmsRowsPerWarp - 1) / (4 * kRmsRowsPerWarp));
+#define MMI_RMS(NVV)                                                                                                   \
+    if (C <= 128 * NVV) {                                                                                              \
+        if (bwd) rmsnorm_bwd_kernel<T, NVV><<<gb, 128, 0, st>>>(xp, w, gp, op, dw, rows, C, x_ld, dy_ld, out_ld, eps); \
+        else rmsnorm_fwd_kernel<T, NVV><<<gf, 128, 0, st>>>(xp, w, op, nullptr, rows, C, x_ld, out_ld, eps);           \
+        return check_cuda(cudaGetLastError(), "rmsnorm launch");                                                      \
+    }
+    MMI_RMS(1)
+    MMI_RMS(2)
+    MMI_RMS(4)
+    MMI_RMS(8)
+#undef MMI_RMS
+    set_error("rmsnorm: C=%d exceeds %d", C, kRmsMaxC);
+    return MMI_ERR_UNSUPPORTED;
+}
+
+}  // namespace mmi
+
+using namespace mmi;
+
+extern "C" {
+
+static int rms_check(const char *who, int64_t rows, int C, int dtype, const void *a, const void *b, int64_t lda, int64_t ldb) {
+    if (rows <= 0 || C <= 0 || C % 8) { set_error("%s: bad shape (rows=%lld C=%d; C must be a multiple of 8)", who, (long long)rows, C); return MMI_ERR_ARG; }
+    const int es = dtype == MMI_F32 ? 4 : (dtype == MMI_BF16 || dtype == MMI_F16) ? 2 : 0;
+    if (!es) { set_error("%s: unknown dtype %d", who, dtype); return MMI_ERR_ARG; }
+    if ((lda * es) % 16 || (ldb * es) % 16 || (reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) {
+        set_error("%s: rows must be 16-byte aligned", who);
+        return MMI_ERR_ARG;
+    }
+    int dev = 0, major = 0;
+    if (int e = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return e;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (major != 10) { set_error("libmmidet_b200 is built for sm_100a only"); return MMI_ERR_UNSUPPORTED; }
+    return MMI_OK;
+}
+
+int mmi_rmsnorm_fwd(const void *x, const float *w, void *y, int64_t rows, int C, int64_t x_ld, int64_t y_ld, float eps, int dtype,
+                    void *stream) {
+    if (!x || !w || !y) { set_error("mmi_rmsnorm_fwd: null pointer"); return MMI_ERR_ARG; }
+    if (int e = rms_check("mmi_rmsnorm_fwd", rows, C, dtype, x, y, x_ld, y_ld)) return e;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (dtype) {
+        case MMI_F32: return rms_launch_t<float>(false, x, w, nullptr, y, nullptr, rows, C, x_ld, 0, y_ld, eps, st);
+        case MMI_BF16: return rms_launch_t<__nv_bfloat16>(false, x, w, nullptr, y, nullptr, rows, C, x_ld, 0, y_ld, eps, st);
+        default: return rms_launch_t<__half>(false, x, w, nullptr, y, nullptr, rows, C, x_ld, 0, y_ld, eps, st);
+    }
+}
+
+int mmi_rmsnorm_bwd(const void *x, const float *w, const void *dy, void *dx, float *dw, int64_t rows, int C, int64_t x_ld,
+                    int64_t dy_ld, int64_t dx_ld, float eps, int dtype, void *stream) {
+    if (!x || !w || !dy || !dx || !dw) { set_error("mmi_rmsnorm_bwd: null pointer"); return MMI_ERR_ARG; }
+    if (int e = rms_check("mmi_rmsnorm_bwd", rows, C, dtype, x, dx, x_ld, dx_ld)) return e;
+    if ((dy_ld * (dtype == MMI_F32 ? 4 : 2)) % 16 || (reinterpret_cast<uintptr_t>(dy) & 15)) { set_error("mmi_rmsnorm_bwd: dy rows must be 16-byte aligned"); return MMI_ERR_ARG; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (dtype) {
+        case MMI_F32: return rms_launch_t<float>(true, x, w, dy, dx, dw, rows, C, x_ld, dy_ld, dx_ld, eps, st);
+        case MMI_BF16: return rms_launch_t<__nv_bfloat16>(true, x, w, dy, dx, dw, rows, C, x_ld, dy_ld, dx_ld, eps, st);
+        default: return rms_launch_t<__half>(true, x, w, dy, dx, dw, rows, C, x_ld, dy_ld, dx_ld, eps, st);
+    }
+}
+
+}  // extern "C"

@@ -170,3 +170,46 @@ def causal_conv1d_silu(x, weight, bias=None, silu: bool = True):
     if x.dtype not in _DT:
         x = x.float()
     return _CausalConv1dSiLU.apply(x, weight, bias, silu)
+
+
+class _RMSNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, eps):
+        global launches
+        lib = _lib.load()
+        _require_cuda(x, "rmsnorm")
+        C = x.shape[-1]
+        x2 = x.reshape(-1, C)
+        if x2.stride(1) != 1 or (x2.stride(0) * x2.element_size()) % 16 or x2.data_ptr() % 16:
+            x2 = x2.contiguous()
+        w = weight.detach().float().contiguous()
+        y = torch.empty((x2.shape[0], C), dtype=x.dtype, device=x.device)
+        _lib.check(lib.mmi_rmsnorm_fwd(_ptr(x2), _ptr(w), _ptr(y), x2.shape[0], C, x2.stride(0), y.stride(0), float(eps),
+                                       _DT[x.dtype], _stream(x)), "mmi_rmsnorm_fwd")
+        launches += 1
+        ctx.save_for_backward(x2, w)
+        ctx.eps, ctx.shape, ctx.wdtype = eps, x.shape, weight.dtype
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        global launches
+        lib = _lib.load()
+        x2, w = ctx.saved_tensors
+        C = x2.shape[1]
+        g = dy.to(x2.dtype).reshape(-1, C)
+        if g.stride(1) != 1 or (g.stride(0) * g.element_size()) % 16 or g.data_ptr() % 16:
+            g = g.contiguous()
+        dx = torch.empty((x2.shape[0], C), dtype=x2.dtype, device=x2.device)
+        dw = torch.empty(C, dtype=torch.float32, device=x2.device)
+        _lib.check(lib.mmi_rmsnorm_bwd(_ptr(x2), _ptr(w), _ptr(g), _ptr(dx), _ptr(dw), x2.shape[0], C, x2.stride(0), g.stride(0),
+                                       dx.stride(0), float(ctx.eps), _DT[x2.dtype], _stream(x2)), "mmi_rmsnorm_bwd")
+        launches += 1
+        return dx.view(ctx.shape), dw.to(ctx.wdtype), None
+
+
+def rmsnorm(x, weight, eps: float = 1e-5):
+    """RMSNorm.forward of models/mamba.py:356-366 as one kernel per direction (x: (..., C), weight: (C))."""
+    if x.dtype not in _DT:
+        x = x.float()
+    return _RMSNorm.apply(x, weight, eps)

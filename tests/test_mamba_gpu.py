@@ -127,3 +127,23 @@ def test_causal_conv1d_silu_vs_oracle(shape, K, dtype, tol):
     assert float(gxz[..., ED:].abs().max()) == 0.0
     assert relerr(gw.cpu().numpy()[:, 0, :], dw) <= max(tol, 2e-5)
     assert relerr(gb.cpu().numpy(), db) <= max(tol, 2e-5)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("rows,C", [(7, 8), (130, 256), (33, 1000), (5, 1024)])
+def test_rmsnorm_vs_torch_fp64(rows, C, dtype, tol):
+    """fused RMSNorm (models/mamba.py:356-366) forward, dx and dw vs the reference formula evaluated in fp64."""
+    from mmidet_b200 import ops
+    torch.manual_seed(rows + C)
+    x = torch.randn(3, rows, C, device="cuda").to(dtype).requires_grad_(True)
+    w = (torch.rand(C, device="cuda") + 0.5).requires_grad_(True)
+    g = torch.randn(3, rows, C, device="cuda").to(dtype)
+    y = ops.rmsnorm(x, w, 1e-5)
+    gx, gw = torch.autograd.grad(y, [x, w], g)
+    xr = x.detach().double().requires_grad_(True)
+    wr = w.detach().double().requires_grad_(True)
+    yr = xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-5) * wr
+    gxr, gwr = torch.autograd.grad(yr, [xr, wr], g.double())
+    assert relerr(y.detach().float().cpu().numpy(), yr.detach().cpu().numpy()) <= tol
+    assert relerr(gx.float().cpu().numpy(), gxr.cpu().numpy()) <= tol
+    assert relerr(gw.float().cpu().numpy(), gwr.cpu().numpy()) <= max(tol, 5e-5)
