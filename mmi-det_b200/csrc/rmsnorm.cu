@@ -11,7 +11,9 @@
 namespace mmi {
 
 constexpr int kRmsMaxC = 1024;           // channels per row held in registers (32 lanes x 4 x 8 float4 groups)
-constexpr int kRmsRowsPerWarp = 16;       // rows per warp strip in the backward (dw is reduced over the strip first)
+constexpr int kRmsRowsPerWarp = 32;       // rows per warp strip in the backward (dw is reduced over the strip, then over the
+                                          // block's four warps in shared memory: the C addresses of dw sit in a handful of L2
+                                          // slices, so every atomic saved matters)
 
 template <typename T> __device__ __forceinline__ void rms_load4(const T *p, float (&v)[4]);
 template <> __device__ __forceinline__ void rms_load4<float>(const float *p, float (&v)[4]) {
@@ -138,12 +140,23 @@ __global__ void __launch_bounds__(128) rmsnorm_bwd_kernel(const T *__restrict__ 
             }
         }
     }
+    __shared__ float red[3][NV * 128];
+    const int warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const int c = (i * 32 + lane) * 4;
-        if (c < C && row0 < rows) {
+    for (int i = 0; i < NV; ++i)
+        if (warp > 0)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) atomicAdd(dw + c + k, dwa[i][k]);
+            for (int k = 0; k < 4; ++k) red[warp - 1][(i * 32 + lane) * 4 + k] = dwa[i][k];
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < C) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    atomicAdd(dw + c + k, dwa[i][k] + red[0][c + k] + red[1][c + k] + red[2][c + k]);
+            }
         }
     }
 }
