@@ -693,10 +693,14 @@ static size_t bwd_seg_header_bytes(int B, int ntile_c) { return (size_t(16) + si
 static size_t al256(size_t v) { return (v + 255) & ~size_t(255); }
 
 // workspace: [dB/dC partials (B, L, ntile_c, 2N)] [dA/dD partials (B, nseg, WT, ED, N+1)] [ticket | flags] [summaries]
+// L is only split when the unsplit grid leaves at least half of the SMs idle (also applied to a forced count), so the
+// per-segment workspaces are sized for kBwdMaxSeg segments only in that case
+static int bwd_seg_cap(int B, int ntile_c) { return int64_t(B) * ntile_c * 2 <= sm_count() ? kBwdMaxSeg : 1; }
 int64_t selscan_bwd_ws_bytes(int B, int L, int ED) {
     const int64_t ntile = (ED + 63) / 64;
-    return int64_t(al256(size_t(B) * L * ntile * 2 * kN * 4)) + int64_t(al256(size_t(B) * kBwdMaxSeg * kBwdWT * ED * (kN + 1) * 4)) +
-           int64_t(bwd_seg_header_bytes(B, int(ntile))) + int64_t(B) * kBwdMaxSeg * ED * (kN + 1) * 4;
+    const int cap = bwd_seg_cap(B, int(ntile));
+    return int64_t(al256(size_t(B) * L * ntile * 2 * kN * 4)) + int64_t(al256(size_t(B) * cap * kBwdWT * ED * (kN + 1) * 4)) +
+           int64_t(bwd_seg_header_bytes(B, int(ntile))) + int64_t(B) * cap * ED * (kN + 1) * 4;
 }
 
 template <typename T> static int launch_bwd_t(BwdParams p, int dtype, void *ws, cudaStream_t st) {
@@ -723,14 +727,15 @@ template <typename T> static int launch_bwd_t(BwdParams p, int dtype, void *ws, 
     const int forced = (p.flags & MMI_FLAG_NSEG_MASK) >> MMI_FLAG_NSEG_SHIFT;
     const int ctas = p.ntile_c * p.B, slots = sm_count();
     int nseg = forced ? forced : (ctas * 2 <= slots ? slots / ctas : 1);
-    nseg = std::max(1, std::min({nseg, kBwdMaxSeg, forced ? ntiles : ntiles / 2}));
+    const int cap = bwd_seg_cap(p.B, p.ntile_c);
+    nseg = std::max(1, std::min({nseg, cap, forced ? ntiles : ntiles / 2}));
     p.seg_tiles = (ntiles + nseg - 1) / nseg;
     p.nseg = (ntiles + p.seg_tiles - 1) / p.seg_tiles;
     char *w = static_cast<char *>(ws);
     p.ws_bc = reinterpret_cast<float *>(w);
     w += al256(size_t(rows) * p.ntile_c * 2 * kN * 4);
     p.ws_ad = reinterpret_cast<float *>(w);
-    w += al256(size_t(p.B) * kBwdMaxSeg * WT * p.ED * (kN + 1) * 4);
+    w += al256(size_t(p.B) * cap * WT * p.ED * (kN + 1) * 4);
     p.seg_ticket = reinterpret_cast<unsigned *>(w);
     p.seg_flags = p.seg_ticket + 4;
     const size_t hdr = bwd_seg_header_bytes(p.B, p.ntile_c);

@@ -451,8 +451,12 @@ constexpr int kMaxSeg = 32;  // upper bound on the number of L segments (sizes t
 
 // workspace of the L split: [ticket | flags (B, nseg, ntile_c)] [summaries (B, nseg, ED, N + 1) fp32]
 static size_t seg_header_bytes(int B, int ntile_c) { return (size_t(16) + size_t(B) * kMaxSeg * ntile_c * 4 + 255) & ~size_t(255); }
+// L is only ever split when the unsplit grid leaves most SMs idle (the heuristic below, also applied to a forced count), so
+// the summaries' workspace is sized for kMaxSeg segments only in that case
+static int fwd_seg_cap(int B, int ntile_c) { return int64_t(B) * ntile_c * 4 <= 2 * sm_count() ? kMaxSeg : 1; }
 int64_t selscan_fwd_ws_bytes(int B, int ED) {
-    return int64_t(seg_header_bytes(B, (ED + 31) / 32)) + int64_t(B) * kMaxSeg * ED * (kN + 1) * 4;
+    const int gx = (ED + 31) / 32;
+    return int64_t(seg_header_bytes(B, gx)) + int64_t(B) * fwd_seg_cap(B, gx) * ED * (kN + 1) * 4;
 }
 
 template <typename T, int WC, int WT, int STAGES, int TCH = kFwdChunk>
@@ -490,7 +494,7 @@ static int launch_fwd_t(FwdParams p, int dtype, void *ws, cudaStream_t st) {
         const int forced = (p.flags & MMI_FLAG_NSEG_MASK) >> MMI_FLAG_NSEG_SHIFT;
         const int ctas = gx * p.B, slots = 2 * sm_count();
         nseg = forced ? forced : (ctas * 4 <= slots ? slots / ctas : 1);  // measured: splitting 128 CTAs in two loses
-        nseg = std::max(1, std::min({nseg, kMaxSeg, forced ? ntiles : ntiles / 2}));
+        nseg = std::max(1, std::min({nseg, fwd_seg_cap(p.B, (p.ED + 31) / 32), forced ? ntiles : ntiles / 2}));
     }
     p.seg_tiles = (ntiles + nseg - 1) / nseg;
     p.nseg = (ntiles + p.seg_tiles - 1) / p.seg_tiles;
