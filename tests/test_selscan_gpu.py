@@ -280,3 +280,14 @@ def test_host_buffer_entry_matches_device_path(B):
     lib.mmi_host_workspace_free()
     for k in ("out", "dx", "ddelta", "dz", "dB", "dC", "dA", "dD"):
         assert relerr(o[k].numpy(), ref[k]) <= 2e-6, k
+
+
+@pytest.mark.parametrize("shape", [(1, 102400, 16), (1, 48, 2560), (3, 1000, 320)])
+def test_extreme_shapes(shape):
+    """the longest sequence and the widest block the detector family implies (L = 102400 tokens at P2 /
+    1280 px, d_inner = 2560 at P5 of YOLOv5x) plus a mid shape that takes the L-split path: outputs and all gradients
+    against the oracle."""
+    B, L, ED = shape
+    inp = scan_inputs(B, L, ED, seed=L % 97 + ED, small_delta=(L > 10000))
+    res = _run(inp)
+    _compare(res, _oracle(inp), TOL32)
