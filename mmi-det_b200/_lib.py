@@ -13,8 +13,8 @@ _DIR = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_DIR)
 SO_PATH = os.path.join(_DIR, "libmmidet_b200.so")
 CSRC = os.path.join(_DIR, "csrc")
-NVCC_FLAGS = ["-t", "8", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
+              "-Xcompiler", "-fvisibility=default"]
 
 MMI_F32, MMI_BF16, MMI_F16 = 0, 1, 2
 FLAG_NO_GEOM = 1
@@ -39,16 +39,37 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> mmi-det_b200/libmmidet_b200.so (in-tree)."""
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> mmi-det_b200/libmmidet_b200.so (in-tree).
+    Every csrc/*.cu is compiled to an object in parallel (the two scan kernels dominate), then linked."""
     if not force and not needs_build():
         return SO_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH] + sources()
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    objdir = os.path.join(_DIR, "build")
+    os.makedirs(objdir, exist_ok=True)
+    hdrs = glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(_ROOT, "include", "*.h"))
+    newest_hdr = max(os.path.getmtime(f) for f in hdrs)
+    log = []
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), newest_hdr):
+            return obj
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + r.stdout + r.stderr)
+        log.append(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(compile_one, sources()))
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO_PATH] + objs,
+                       capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
     if verbose:
-        print(r.stderr)
+        print("".join(log))
     return SO_PATH
 
 

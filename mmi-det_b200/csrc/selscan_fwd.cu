@@ -514,16 +514,16 @@ static int launch_fwd_t(FwdParams p, int dtype, void *ws, cudaStream_t st) {
 
 int selscan_fwd_launch(const FwdParams &p, int dtype, void *ws, cudaStream_t st) {
     const int cfg = (p.flags & MMI_FLAG_CFG_MASK) >> MMI_FLAG_CFG_SHIFT;
-#define MMI_FWD_DISPATCH(T)                                        \
-    switch (cfg) {                                                 \
-        case 1: return launch_fwd_t<T, 2, 4, 3>(p, dtype, ws, st);     \
-        case 2: return launch_fwd_t<T, 1, 8, 2>(p, dtype, ws, st);     \
-        case 3: return launch_fwd_t<T, 1, 2, 4>(p, dtype, ws, st);     \
-        case 4: return launch_fwd_t<T, 1, 8, 3, 8>(p, dtype, ws, st);  \
-        case 5: return launch_fwd_t<T, 1, 8, 4, 8>(p, dtype, ws, st);  \
-        case 6: return launch_fwd_t<T, 2, 8, 2, 8>(p, dtype, ws, st);  \
-        default: return launch_fwd_t<T, 1, 4, 3>(p, dtype, ws, st);    \
+#define MMI_FWD_DISPATCH(T)                                            \
+    switch (std::is_same<T, float>::value ? cfg : 0) {                 \
+        case 1: return launch_fwd_t<float, 2, 4, 3>(p, dtype, ws, st);     \
+        case 2: return launch_fwd_t<float, 1, 8, 2>(p, dtype, ws, st);     \
+        case 3: return launch_fwd_t<float, 1, 2, 4>(p, dtype, ws, st);     \
+        case 4: return launch_fwd_t<float, 1, 8, 3, 8>(p, dtype, ws, st);  \
+        case 6: return launch_fwd_t<float, 2, 8, 2, 8>(p, dtype, ws, st);  \
+        default: return launch_fwd_t<T, 1, 4, 3>(p, dtype, ws, st);        \
     }
+    // (the alternative CTA shapes exist for tuning runs and shape tests: fp32 only)
     switch (dtype) {
         case MMI_F32: MMI_FWD_DISPATCH(float)
         case MMI_BF16: MMI_FWD_DISPATCH(__nv_bfloat16)

@@ -59,7 +59,7 @@ def _compare(res, ref, tol, keys=None):
     assert not bad, f"rel-err above {tol}: {bad}"
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 6])
 @pytest.mark.parametrize("random_A", [False, True])
 @pytest.mark.parametrize("shape", [(2, 96, 64), (1, 16, 8), (3, 37, 24), (2, 257, 40), (1, 1, 16), (2, 15, 72), (1, 300, 104)])
 def test_fwd_bwd_fp32_vs_oracle(shape, random_A, cfg):
@@ -82,7 +82,7 @@ def test_forced_general_path_on_geometric_A(cfg):
     _compare(b, ref, TOL32)
 
 
-@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 6])
 @pytest.mark.parametrize("random_A", [False, True])
 def test_cta_shapes_agree(cfg, random_A):
     """The time axis is scanned by several warps per CTA (chunk summaries chained through shared memory); every CTA
