@@ -21,31 +21,6 @@ static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
     return fn;
 }
 
-int make_tmap_2d(CUtensorMap *map, const void *base, int dtype, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
-                 uint32_t box_rows, uint32_t box_cols) {
-    auto fn = encode_fn();
-    if (!fn) {
-        set_error("cuTensorMapEncodeTiled is not available from the installed driver");
-        return MMI_ERR_CUDA;
-    }
-    CUtensorMapDataType dt = dtype == MMI_F32    ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
-                             : dtype == MMI_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
-                                                 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-    const cuuint64_t dims[2] = {cols, rows};
-    const cuuint64_t strides[1] = {pitch_bytes};
-    const cuuint32_t box[2] = {box_cols, box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu pitch=%llu box=%ux%u)", int(r),
-                  (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch_bytes, box_rows, box_cols);
-        return MMI_ERR_CUDA;
-    }
-    return MMI_OK;
-}
-
-
 int encode_tmap_3d(CUtensorMap *map, const void *base, int dtype, uint64_t nb, uint64_t L, uint64_t cols, uint64_t pitch_bytes,
                    uint32_t box_rows, uint32_t box_cols);
 
