@@ -141,6 +141,16 @@ int mmi_rmsnorm_bwd(const void *x, const float *w, const void *dy, void *dx, flo
                     int64_t dy_ld, int64_t dx_ld, float eps, int dtype, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Token layout either side of the fusion block.  Replaces flatten / cat / permute / contiguous of
+ * models/common.py:1338-1343 and the split / reshape back of :1352-1366:
+ *     gather : tok[b, m*HW + p, c] = (m == 0 ? rgb : ir)[b, c, p]      rgb, ir (B, C, HW) contiguous (NCHW maps)
+ *     scatter: the inverse (and the adjoint: each is the other's backward)        tok (B, 2*HW, C) contiguous
+ * Any 2- or 4-byte dtype; pure data movement through a shared-memory tile transpose.
+ * --------------------------------------------------------------------------------------------------------- */
+int mmi_tokens_gather(const void *rgb, const void *ir, void *tok, int B, int C, int HW, int dtype, void *stream);
+int mmi_tokens_scatter(const void *tok, void *rgb, void *ir, int B, int C, int HW, int dtype, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Host-buffer entry (end-to-end path used by bench.py `e2e`): same maths as mmi_selscan_fwd followed by
  * mmi_selscan_bwd, with every pointer a HOST pointer (pinned memory recommended).  Copies inputs H2D, runs
  * forward + backward on an internal stream, copies out/dx/ddelta/dz/dB/dC/dA/dD back and synchronises.

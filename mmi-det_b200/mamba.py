@@ -196,7 +196,12 @@ class MambaFusion(nn.Module):
     def forward(self, x):
         rgb, ir = x[0], x[1]
         B, C, H, W = rgb.shape
-        tok = torch.cat([rgb.flatten(2), ir.flatten(2)], dim=2).transpose(1, 2).contiguous()  # (B, 2HW, C), VIS then IR
+        if rgb.is_cuda and rgb.dtype in ops._DT and rgb.dtype == ir.dtype:
+            tok = ops.tokens_gather(rgb, ir)  # (B, 2HW, C), VIS tokens then IR tokens: one tiled transpose
+            for layer in self.layers:
+                tok = layer(tok)
+            return ops.tokens_scatter(tok, (B, C, H, W))
+        tok = torch.cat([rgb.flatten(2), ir.flatten(2)], dim=2).transpose(1, 2).contiguous()  # same layout, plain torch glue
         for layer in self.layers:
             tok = layer(tok)
         out = tok.transpose(1, 2).reshape(B, C, 2, H, W)

@@ -213,3 +213,63 @@ def rmsnorm(x, weight, eps: float = 1e-5):
     if x.dtype not in _DT:
         x = x.float()
     return _RMSNorm.apply(x, weight, eps)
+
+
+def _tok_gather(rgb, ir):
+    global launches
+    lib = _lib.load()
+    B, C = rgb.shape[0], rgb.shape[1]
+    HW = rgb[0, 0].numel()
+    rgb, ir = rgb.contiguous(), ir.contiguous()
+    tok = torch.empty((B, 2 * HW, C), dtype=rgb.dtype, device=rgb.device)
+    _lib.check(lib.mmi_tokens_gather(_ptr(rgb), _ptr(ir), _ptr(tok), B, C, HW, _DT[rgb.dtype], _stream(rgb)), "mmi_tokens_gather")
+    launches += 1
+    return tok
+
+
+def _tok_scatter(tok, shape):
+    global launches
+    lib = _lib.load()
+    B, C = shape[0], shape[1]
+    HW = tok.shape[1] // 2
+    tok = tok.contiguous()
+    rgb = torch.empty(shape, dtype=tok.dtype, device=tok.device)
+    ir = torch.empty(shape, dtype=tok.dtype, device=tok.device)
+    _lib.check(lib.mmi_tokens_scatter(_ptr(tok), _ptr(rgb), _ptr(ir), B, C, HW, _DT[tok.dtype], _stream(tok)), "mmi_tokens_scatter")
+    launches += 1
+    return rgb, ir
+
+
+class _TokensGather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rgb, ir):
+        ctx.shape = rgb.shape
+        return _tok_gather(rgb, ir)
+
+    @staticmethod
+    def backward(ctx, dtok):
+        return _tok_scatter(dtok, ctx.shape)
+
+
+class _TokensScatter(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tok, shape):
+        return _tok_scatter(tok, shape)
+
+    @staticmethod
+    def backward(ctx, drgb, dir_):
+        return _tok_gather(drgb, dir_), None
+
+
+def tokens_gather(rgb, ir):
+    """Two NCHW maps (B, C, H, W) -> channels-last tokens (B, 2*H*W, C), VIS tokens first then IR (models/common.py:1338-1343)."""
+    _require_cuda(rgb, "tokens_gather")
+    if rgb.dtype not in _DT or rgb.shape != ir.shape or rgb.dtype != ir.dtype:
+        raise RuntimeError("tokens_gather: rgb and ir must have the same shape and a float dtype")
+    return _TokensGather.apply(rgb, ir)
+
+
+def tokens_scatter(tok, shape):
+    """Inverse of tokens_gather: tokens (B, 2*H*W, C) -> (rgb, ir) of `shape` = (B, C, H, W) (models/common.py:1352-1366)."""
+    _require_cuda(tok, "tokens_scatter")
+    return _TokensScatter.apply(tok, tuple(shape))

@@ -147,3 +147,24 @@ def test_rmsnorm_vs_torch_fp64(rows, C, dtype, tol):
     assert relerr(y.detach().float().cpu().numpy(), yr.detach().cpu().numpy()) <= tol
     assert relerr(gx.float().cpu().numpy(), gxr.cpu().numpy()) <= tol
     assert relerr(gw.float().cpu().numpy(), gwr.cpu().numpy()) <= max(tol, 5e-5)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 16, 6, 5), (1, 72, 7, 9), (3, 256, 20, 20)])
+def test_tokens_gather_scatter(shape, dtype):
+    """token layout kernels == flatten / cat / transpose of models/common.py:1338-1343 (bit-exact: pure data movement), the
+    scatter inverts the gather, and each is the other's adjoint under autograd."""
+    from mmidet_b200 import ops
+    B, C, H, W = shape
+    torch.manual_seed(C)
+    rgb = torch.randn(shape, device="cuda").to(dtype).requires_grad_(True)
+    ir = torch.randn(shape, device="cuda").to(dtype).requires_grad_(True)
+    tok = ops.tokens_gather(rgb, ir)
+    ref = torch.cat([rgb.flatten(2), ir.flatten(2)], dim=2).transpose(1, 2)
+    assert torch.equal(tok, ref)
+    r2, i2 = ops.tokens_scatter(tok, shape)
+    assert torch.equal(r2, rgb) and torch.equal(i2, ir)
+    g = torch.randn_like(tok)
+    gr, gi = torch.autograd.grad(tok, [rgb, ir], g)
+    gr_ref, gi_ref = torch.autograd.grad(ref, [rgb, ir], g)
+    assert torch.equal(gr, gr_ref) and torch.equal(gi, gi_ref)
