@@ -6,7 +6,7 @@
 namespace mmi {
 
 constexpr int kChunk = 16;     // state-checkpoint interval in timesteps == the chunk one backward warp scans per super-tile
-constexpr int kFwdChunk = 16;  // chunk one forward warp scans per super-tile (a multiple of kChunk)
+constexpr int kFwdChunk = 16;  // default chunk one forward warp scans per super-tile (shape-test configs also use 8)
 
 struct FwdParams {
     const void *x, *delta, *z, *Bm, *Cm;

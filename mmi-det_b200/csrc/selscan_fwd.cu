@@ -11,7 +11,7 @@
 // Mapping.  One lane owns one channel d and its N = 16 states in registers (channels-last layout: a warp reads 32
 // adjacent channels of a timestep).  The only thing that is serial in t is h = a*h + u, and B*ED rows alone
 // do not fill 148 SMs, so the time axis is parallelised INSIDE the CTA: a CTA owns CH = 32*WC channels of one batch
-// element and walks L in super-tiles of ST = WT*kChunk steps; warp (wc, wt) owns chunk wt of the super-tile.  Tiles
+// element and walks L in super-tiles of ST = WT*TC steps (TC = 16); warp (wc, wt) owns chunk wt of the super-tile.  Tiles
 // [ST x CH] of x / delta / z and [ST x N] of B / C are staged by the TMA engine (3-D tensor maps, one mbarrier per
 // stage, a STAGES-deep ring), so HBM latency is covered by bytes in flight rather than by thread count.  Per super-tile:
 //   sweep A  each warp reduces its chunk to (local end state E, sum of delta) by direct evaluation
