@@ -307,3 +307,36 @@ def test_geometric_rows_with_per_channel_base_and_large_delta():
     _compare(res, ref, TOL32)
     forced = _run(inp, flags=1)  # general 16-exponential path on the same data
     _compare(forced, ref, TOL32)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_fuzz_against_oracle(seed):
+    """seeded random shapes x gate / no gate x fused softplus x general / geometric A x forced CTA shape and L split:
+    forward output and every gradient against the oracle (fp32 tolerance)."""
+    from mmidet_b200 import ops
+    rng = np.random.default_rng(1000 + seed)
+    B = int(rng.integers(1, 4))
+    L = int(rng.choice([1, 2, 15, 16, 17, 63, 64, 65, 100, 129, 250, 511, 700]))
+    ED = int(rng.choice([8, 16, 24, 40, 64, 72, 104, 136]))
+    gate, sp, random_A = bool(rng.integers(2)), bool(rng.integers(2)), bool(rng.integers(2))
+    cfg = int(rng.choice([0, 0, 1, 2, 3, 4, 6]))
+    nseg = int(rng.choice([0, 0, 1, 2, 3, 7]))
+    flags = (cfg << 4) | (nseg << 8)
+    inp = scan_inputs(B, L, ED, seed=seed, random_A=random_A)
+    ref_in = dict(inp)
+    if sp:
+        pre = (rng.standard_normal((B, L, ED)) * 1.5 - 2.5).astype(np.float32)
+        ref_in["delta"] = np.log1p(np.exp(pre.astype(np.float64)))
+    ref = _oracle(ref_in, gate=gate)
+    if sp:
+        ref["ddelta"] = ref["ddelta"] / (1.0 + np.exp(-pre.astype(np.float64)))
+    leaves = {k: _t(inp[k]).requires_grad_(True) for k in ("x", "z", "A", "Bm", "Cm", "D")}
+    tdel = _t(pre if sp else inp["delta"]).requires_grad_(True)
+    out = ops.selective_scan(leaves["x"], tdel, leaves["A"], leaves["Bm"], leaves["Cm"], leaves["D"],
+                             z=leaves["z"] if gate else None, flags=flags, delta_softplus=sp)
+    out.backward(_t(inp["dout"]))
+    res = {"out": out.detach().cpu().numpy(), "ddelta": tdel.grad.cpu().numpy()}
+    for k, n in dict(x="dx", z="dz", A="dA", Bm="dB", Cm="dC", D="dD").items():
+        if leaves[k].grad is not None:
+            res[n] = leaves[k].grad.cpu().numpy()
+    _compare(res, ref, TOL32)
