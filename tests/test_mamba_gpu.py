@@ -168,3 +168,20 @@ def test_tokens_gather_scatter(shape, dtype):
     gr, gi = torch.autograd.grad(tok, [rgb, ir], g)
     gr_ref, gi_ref = torch.autograd.grad(ref, [rgb, ir], g)
     assert torch.equal(gr, gr_ref) and torch.equal(gi, gi_ref)
+
+
+def test_graphed_fusion_matches_eager():
+    """CUDA-graph replay of a fusion block (inference): same outputs as the eager call, for two different inputs of the same
+    shape (replay reads the new data) and for a second shape (second graph)."""
+    from mmidet_b200.graphs import Graphed
+    from mmidet_b200.mamba import MambaFusion
+    torch.manual_seed(0)
+    fus = MambaFusion(64).cuda().eval()
+    fast = Graphed(fus)
+    for shape in ((1, 64, 12, 12), (1, 64, 12, 12), (2, 64, 7, 9)):
+        x = [torch.randn(shape, device="cuda"), torch.randn(shape, device="cuda")]
+        with torch.no_grad():
+            a, b = fus(x)
+        c, d = fast(x)
+        assert torch.allclose(a, c, atol=1e-6, rtol=1e-5) and torch.allclose(b, d, atol=1e-6, rtol=1e-5)
+    assert len(fast._graphs) == 2
