@@ -116,6 +116,44 @@ void mmi_ffm_kept_range(int H, int W, int *r0, int *r1, int *c0, int *c1);
 int mmi_separation_loss(const float *M, float *loss, int l, int K, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Pattern path of the Fusion Focus Module between the pooling and the transformer.  Replaces, in
+ * GPT1_fourier.forward, models/common.py:440-455 (conv1 + sigmoid of high*fea), :476-480 (conv1 + sigmoid of the
+ * pooled maps), :487-490 (the row set handed to Seperation_loss) and :496-516 (conv2(M) * fea, flatten, concat,
+ * permute to tokens), for both modalities in one launch:
+ *     M = sigmoid(W1 fea),  tok[b, m*P + p, c] = (W2 M)[c, p] * fea[b, c, p],  m = 0 (VIS), 1 (IR)
+ *     rows = [M_vis (8B rows); M_ir (8B); sigmoid(W1 hm_vis).view(-1, P)[:B]; sigmoid(W1 hm_ir).view(-1, P)[:B]]
+ *   fea_vis, fea_ir (B, C, H, W) dtype contiguous (the pooled maps, P = H*W = vert_anchors * horz_anchors <= 128);
+ *   W1 (8, C) = conv1.weight, W2 (C, 8) = conv2.weight, fp32; tok (B, 2P, C) dtype; rows (18B, P) fp32;
+ *   loss (nullable) fp32[1] = Seperation_loss(rows) (models/common.py:494).  hm = high * fea is needed only for the
+ *   first ceil(B / 8) batch entries (len // 8 rows reach the loss, common.py:487); the call computes it into ws.
+ *   Three launches: high-pass product (both modalities), pattern kernel (grid B x 2), separation loss.
+ * The backward differentiates the token path (the reference detaches the pattern loss, models/yolo_test.py:230):
+ *   dtok (B, 2P, C) dtype -> dfea_vis, dfea_ir (B, C, P) dtype, dW1 (8, C), dW2 (C, 8) fp32 (overwritten; summed in a
+ *   fixed order from per-CTA partials in ws).  rows is the forward's output.
+ *   ws: mmi_ffm_pattern_ws_bytes(B, C, P) bytes, either direction.
+ * --------------------------------------------------------------------------------------------------------- */
+int64_t mmi_ffm_pattern_ws_bytes(int B, int C, int P);
+int mmi_ffm_pattern_fwd(const void *fea_vis, const void *fea_ir, const float *W1, const float *W2, void *tok, float *rows,
+                        float *loss, void *ws, int B, int C, int H, int W, int dtype, void *stream);
+int mmi_ffm_pattern_bwd(const void *fea_vis, const void *fea_ir, const void *dtok, const float *rows, const float *W1,
+                        const float *W2, void *dfea_vis, void *dfea_ir, float *dW1, float *dW2, void *ws, int B, int C,
+                        int P, int dtype, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Resampling either side of the FFM token path.  Replace nn.AdaptiveAvgPool2d((vert_anchors, horz_anchors))
+ * (models/common.py:324-325, applied at :396-397) and F.interpolate(size=(H, W), mode='bilinear') with the default
+ * align_corners=False (models/common.py:540-543), forward and backward:
+ *   big (BC, H, W), small (BC, hs, ws), both dtype contiguous; hs * ws <= 256, H, W <= 2048; pooling needs H >= hs, W >= ws.
+ *   mmi_avgpool_fwd: big -> small;  mmi_avgpool_bwd: d small -> d big;
+ *   mmi_upsample_bilinear_fwd: small -> big;  mmi_upsample_bilinear_bwd: d big -> d small.
+ * One CTA per (b, c) image, the big map crosses HBM once, fp32 accumulation in a fixed order (no atomics).
+ * --------------------------------------------------------------------------------------------------------- */
+int mmi_avgpool_fwd(const void *big, void *small, int BC, int H, int W, int hs, int ws, int dtype, void *stream);
+int mmi_avgpool_bwd(const void *dsmall, void *dbig, int BC, int H, int W, int hs, int ws, int dtype, void *stream);
+int mmi_upsample_bilinear_fwd(const void *small, void *big, int BC, int H, int W, int hs, int ws, int dtype, void *stream);
+int mmi_upsample_bilinear_bwd(const void *dbig, void *dsmall, int BC, int H, int W, int hs, int ws, int dtype, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Depthwise causal conv1d (+ bias) + SiLU on channels-last tokens.  Replaces the x-branch prologue of
  * MambaBlock.forward (models/mamba.py:176-180): transpose -> nn.Conv1d(ED, ED, K, groups=ED, padding=K-1)[..., :L]
  * -> transpose -> F.silu, without the transposes:

@@ -91,6 +91,13 @@ _SIGNATURES = {
     "mmi_ffm_kept_range": (None, [_i, _i] + [_c.POINTER(_i)] * 4),
     "mmi_ffm_extract": (_i, [_vp] * 4 + [_i] * 4 + [_vp]),
     "mmi_separation_loss": (_i, [_vp] * 2 + [_i] * 2 + [_vp]),
+    "mmi_ffm_pattern_ws_bytes": (_i64, [_i, _i, _i]),
+    "mmi_avgpool_fwd": (_i, [_vp] * 2 + [_i] * 6 + [_vp]),
+    "mmi_avgpool_bwd": (_i, [_vp] * 2 + [_i] * 6 + [_vp]),
+    "mmi_upsample_bilinear_fwd": (_i, [_vp] * 2 + [_i] * 6 + [_vp]),
+    "mmi_upsample_bilinear_bwd": (_i, [_vp] * 2 + [_i] * 6 + [_vp]),
+    "mmi_ffm_pattern_fwd": (_i, [_vp] * 8 + [_i] * 5 + [_vp]),
+    "mmi_ffm_pattern_bwd": (_i, [_vp] * 11 + [_i] * 4 + [_vp]),
     "mmi_causal_conv1d_fwd": (_i, [_vp] * 4 + [_i] * 4 + [_i64] * 2 + [_i] * 2 + [_vp]),
     "mmi_causal_conv1d_bwd": (_i, [_vp] * 7 + [_i] * 4 + [_i64] * 3 + [_i] * 2 + [_vp]),
     "mmi_rmsnorm_fwd": (_i, [_vp] * 3 + [_i64, _i, _i64, _i64, _c.c_float, _i, _vp]),

@@ -85,6 +85,16 @@ int ffm_extract_launch(const void *img, void *low, void *high, float *high_mul, 
                        cudaStream_t st);
 int separation_loss_launch(const float *M, float *loss, int l, int K, cudaStream_t st);
 void ffm_kept_range(int H, int W, int *r0, int *r1, int *c0, int *c1);
+int resample_reduce_launch(const void *big, void *small, int BC, int H, int W, int hs, int ws, int mode, int dtype,
+                           cudaStream_t st, const char *fn);
+int resample_expand_launch(const void *small, void *big, int BC, int H, int W, int hs, int ws, int mode, int dtype,
+                           cudaStream_t st, const char *fn);
+int64_t ffm_pattern_ws_bytes(int B, int C, int P);
+int ffm_pattern_fwd_launch(const void *fea_vis, const void *fea_ir, const float *W1, const float *W2, void *tok, float *rows,
+                           float *loss, float *ws, int B, int C, int H, int W, int dtype, cudaStream_t st);
+int ffm_pattern_bwd_launch(const void *fea_vis, const void *fea_ir, const void *dtok, const float *rows, const float *W1,
+                           const float *W2, void *dfea_vis, void *dfea_ir, float *dW1, float *dW2, float *ws, int B, int C,
+                           int P, int dtype, cudaStream_t st);
 
 }  // namespace mmi
 
@@ -205,6 +215,39 @@ int mmi_separation_loss(const float *M, float *loss, int l, int K, void *stream)
     if (l < 2 || K < 1) { set_error("mmi_separation_loss: need l >= 2 rows and K >= 1 columns (l=%d K=%d)", l, K); return MMI_ERR_ARG; }
     if (int e = require_device()) return e;
     return separation_loss_launch(M, loss, l, K, static_cast<cudaStream_t>(stream));
+}
+
+#define MMI_RESAMPLE_ENTRY(NAME, SRC, DST, LAUNCH, MODE)                                                             \
+    int NAME(const void *SRC, void *DST, int BC, int H, int W, int hs, int ws, int dtype, void *stream) {              \
+        if (!SRC || !DST) { set_error(#NAME ": null pointer"); return MMI_ERR_ARG; }                                    \
+        if (!elem_size(dtype)) { set_error(#NAME ": unknown dtype %d", dtype); return MMI_ERR_ARG; }                    \
+        if (int e = require_device()) return e;                                                                         \
+        return LAUNCH(SRC, DST, BC, H, W, hs, ws, MODE, dtype, static_cast<cudaStream_t>(stream), #NAME);               \
+    }
+MMI_RESAMPLE_ENTRY(mmi_avgpool_fwd, big, small, resample_reduce_launch, 0)
+MMI_RESAMPLE_ENTRY(mmi_avgpool_bwd, dsmall, dbig, resample_expand_launch, 0)
+MMI_RESAMPLE_ENTRY(mmi_upsample_bilinear_fwd, small, big, resample_expand_launch, 1)
+MMI_RESAMPLE_ENTRY(mmi_upsample_bilinear_bwd, dbig, dsmall, resample_reduce_launch, 1)
+#undef MMI_RESAMPLE_ENTRY
+
+int64_t mmi_ffm_pattern_ws_bytes(int B, int C, int P) { return B > 0 && C > 0 && P > 0 ? ffm_pattern_ws_bytes(B, C, P) : 0; }
+
+int mmi_ffm_pattern_fwd(const void *fea_vis, const void *fea_ir, const float *W1, const float *W2, void *tok, float *rows,
+                        float *loss, void *ws, int B, int C, int H, int W, int dtype, void *stream) {
+    if (!fea_vis || !fea_ir || !W1 || !W2 || !tok || !rows || !ws) { set_error("mmi_ffm_pattern_fwd: null pointer"); return MMI_ERR_ARG; }
+    if (H < 1 || W < 1) { set_error("mmi_ffm_pattern_fwd: pooled map %dx%d", H, W); return MMI_ERR_ARG; }
+    if (!elem_size(dtype)) { set_error("mmi_ffm_pattern_fwd: unknown dtype %d", dtype); return MMI_ERR_ARG; }
+    if (int e = require_device()) return e;
+    return ffm_pattern_fwd_launch(fea_vis, fea_ir, W1, W2, tok, rows, loss, static_cast<float *>(ws), B, C, H, W, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int mmi_ffm_pattern_bwd(const void *fea_vis, const void *fea_ir, const void *dtok, const float *rows, const float *W1,
+                        const float *W2, void *dfea_vis, void *dfea_ir, float *dW1, float *dW2, void *ws, int B, int C,
+                        int P, int dtype, void *stream) {
+    if (!fea_vis || !fea_ir || !dtok || !rows || !W1 || !W2 || !dfea_vis || !dfea_ir || !dW1 || !dW2 || !ws) { set_error("mmi_ffm_pattern_bwd: null pointer"); return MMI_ERR_ARG; }
+    if (!elem_size(dtype)) { set_error("mmi_ffm_pattern_bwd: unknown dtype %d", dtype); return MMI_ERR_ARG; }
+    if (int e = require_device()) return e;
+    return ffm_pattern_bwd_launch(fea_vis, fea_ir, dtok, rows, W1, W2, dfea_vis, dfea_ir, dW1, dW2, static_cast<float *>(ws), B, C, P, dtype, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

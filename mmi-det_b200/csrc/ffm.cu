@@ -18,7 +18,13 @@ constexpr int kFfmMax = 64;
 template <typename T>
 __global__ void __launch_bounds__(128) ffm_extract_kernel(const T *__restrict__ img, __half *__restrict__ low,
                                                           __half *__restrict__ high, float *__restrict__ high_mul, int H,
-                                                          int W, int r0, int r1, int c0, int c1) {
+                                                          int W, int r0, int r1, int c0, int c1,
+                                                          const T *__restrict__ img2 = nullptr,
+                                                          float *__restrict__ high_mul2 = nullptr) {
+    if (blockIdx.y) {  // second modality of the pattern path (product only)
+        img = img2;
+        high_mul = high_mul2;
+    }
     extern __shared__ float sm[];
     float *x = sm;               // [H][W]
     float *tre = x + H * W;      // [H][W]  T = x . Pc^T (complex)
@@ -75,8 +81,8 @@ __global__ void __launch_bounds__(128) ffm_extract_kernel(const T *__restrict__ 
         }
         const float xv = x[i];
         const __half l16 = __float2half_rn(lo), h16 = __float2half_rn(xv - lo);
-        low[off + i] = l16;
-        high[off + i] = h16;
+        if (low) low[off + i] = l16;
+        if (high) high[off + i] = h16;
         if (high_mul) high_mul[off + i] = __half2float(h16) * xv;  // torch.mul(high.half(), fea) -> fp32
     }
 }
@@ -85,15 +91,38 @@ __global__ void __launch_bounds__(128) ffm_extract_kernel(const T *__restrict__ 
 __global__ void __launch_bounds__(256) separation_loss_kernel(const float *__restrict__ M, float *__restrict__ loss, int l,
                                                               int K) {
     __shared__ float red[256];
+    __shared__ float part[2][256];
     float acc = 0.f;
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    if (K <= 128) {  // the pattern path: K = 64 columns, up to 18 * B rows -- split the rows over 256 / K thread groups
+        const int G = 256 / K, g = threadIdx.x / K, k = threadIdx.x % K;
         float s = 0.f, q = 0.f;
-        for (int i = 0; i < l; ++i) {
-            const float v = M[int64_t(i) * K + k];
-            s += v;
-            q = fmaf(v, v, q);
+        if (g < G)
+            for (int i = g; i < l; i += G) {
+                const float v = M[int64_t(i) * K + k];
+                s += v;
+                q = fmaf(v, v, q);
+            }
+        part[0][threadIdx.x] = s;
+        part[1][threadIdx.x] = q;
+        __syncthreads();
+        if (threadIdx.x < K) {
+            s = 0.f, q = 0.f;
+            for (int gg = 0; gg < G; ++gg) {
+                s += part[0][gg * K + k];
+                q += part[1][gg * K + k];
+            }
+            acc = s * s - q;
         }
-        acc += s * s - q;  // column k of |sum_i M_i|^2 - sum_i |M_i|^2
+    } else {
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            float s = 0.f, q = 0.f;
+            for (int i = 0; i < l; ++i) {
+                const float v = M[int64_t(i) * K + k];
+                s += v;
+                q = fmaf(v, v, q);
+            }
+            acc += s * s - q;  // column k of |sum_i M_i|^2 - sum_i |M_i|^2
+        }
     }
     red[threadIdx.x] = acc;
     __syncthreads();
@@ -138,7 +167,7 @@ int ffm_extract_launch(const void *img, void *low, void *high, float *high_mul, 
             if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)), \
                                    "ffm smem attribute"))                                                               \
                 return e;                                                                                               \
-        kern<<<BC, 128, smem, st>>>(static_cast<const T *>(img), lo, hi, high_mul, H, W, r0, r1, c0, c1);               \
+        kern<<<BC, 128, smem, st>>>(static_cast<const T *>(img), lo, hi, high_mul, H, W, r0, r1, c0, c1, nullptr, nullptr); \
     } while (0)
     switch (dtype) {
         case MMI_F32: MMI_FFM_LAUNCH(float); break;
@@ -148,6 +177,30 @@ int ffm_extract_launch(const void *img, void *low, void *high, float *high_mul, 
     }
 #undef MMI_FFM_LAUNCH
     return check_cuda(cudaGetLastError(), "ffm_extract launch");
+}
+
+// high * fea (fp32) of both modalities in one launch: the only part of the Fourier split the pattern path consumes.
+int ffm_highmul_pair_launch(const void *vis, const void *ir, float *hm_vis, float *hm_ir, int BC, int H, int W, int dtype,
+                            cudaStream_t st) {
+    if (H > kFfmMax || W > kFfmMax || H < 1 || W < 1) {
+        set_error("mmi_ffm_pattern_fwd: pooled map must be within [1, %d]^2 (got %dx%d)", kFfmMax, H, W);
+        return MMI_ERR_UNSUPPORTED;
+    }
+    int r0, r1, c0, c1;
+    ffm_kept_range(H, W, &r0, &r1, &c0, &c1);
+    const size_t smem = (size_t(3) * H * W + 2 * (H + W)) * sizeof(float);  // <= 48 KB whenever H*W <= 128
+    const dim3 grid(BC, 2);
+#define MMI_FFM_PAIR(T)                                                                                                 \
+    ffm_extract_kernel<T><<<grid, 128, smem, st>>>(static_cast<const T *>(vis), nullptr, nullptr, hm_vis, H, W, r0, r1, c0, \
+                                                  c1, static_cast<const T *>(ir), hm_ir)
+    switch (dtype) {
+        case MMI_F32: MMI_FFM_PAIR(float); break;
+        case MMI_BF16: MMI_FFM_PAIR(__nv_bfloat16); break;
+        case MMI_F16: MMI_FFM_PAIR(__half); break;
+        default: set_error("mmi_ffm_pattern_fwd: unknown dtype %d", dtype); return MMI_ERR_ARG;
+    }
+#undef MMI_FFM_PAIR
+    return check_cuda(cudaGetLastError(), "ffm high-pass product launch");
 }
 
 int separation_loss_launch(const float *M, float *loss, int l, int K, cudaStream_t st) {

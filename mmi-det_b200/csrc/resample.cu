@@ -1,0 +1,388 @@
+// resample.cu -- the two resampling steps either side of the FFM token path:
+//   AdaptiveAvgPool2d((vert_anchors, horz_anchors)) of the (B, C, H, W) maps   (models/common.py:324-325, :396-397)
+//   F.interpolate(size=(H, W), mode='bilinear') of the (B, C, 8, 8) outputs     (models/common.py:540-543)
+// Both are separable linear maps between a big grid (H, W) and a small anchor grid (hs, ws) in which every big-grid
+// index touches at most two small-grid indices (a pooling window pair / the two bilinear taps):
+//     reduce:  small[i, j] = sum_{y, x} Wy[i, y] Wx[j, x] big[y, x]     (pool forward, upsample backward)
+//     expand:  big[y, x]   = sum_{i, j} Wy[i, y] Wx[j, x] small[i, j]   (upsample forward, pool backward)
+// so two kernels cover the four directions; each streams the big map through HBM exactly once (one CTA per (b, c)
+// image, fp32 accumulation, fixed summation order -- no atomics).  The stock backward of the bilinear upsample
+// scatters 25600 gradients per image onto 64 addresses with global atomics (12 ms at B=16, C=128, 160x160 fp32 on
+// B200, profiles/r01_ffm_module.txt); the reduce kernel reads the gradient once.
+#include "../../include/mmidet_b200.h"
+#include "common.cuh"
+
+namespace mmi {
+
+constexpr int kRsThreads = 256;
+constexpr int kRsRows = 16;        // big-grid rows per tile in the reduce kernel
+constexpr int kRsMaxSmall = 256;   // hs * ws
+constexpr int kRsMaxBig = 2048;    // H, W
+
+enum { RS_POOL = 0, RS_BILINEAR = 1 };
+
+// taps of big-grid index `p` (extent n) on the small grid (extent ns): indices i0 <= i1 and weights w0, w1.
+__device__ __forceinline__ void taps(int mode, int p, int n, int ns, int &i0, int &i1, float &w0, float &w1) {
+    if (mode == RS_POOL) {
+        // adaptive windows [floor(j n / ns), ceil((j + 1) n / ns)): p lies in windows lo..hi, hi - lo <= 1 for n >= ns
+        const int lo = int((int64_t(p) * ns) / n), hi = int((int64_t(p + 1) * ns - 1) / n);
+        auto inv_len = [&](int j) {
+            const int s = int((int64_t(j) * n) / ns), e = int((int64_t(j + 1) * n + ns - 1) / ns);
+            return 1.0f / float(e - s);
+        };
+        i0 = lo;
+        i1 = hi;
+        w0 = inv_len(lo);
+        w1 = hi != lo ? inv_len(hi) : 0.f;
+    } else {
+        // align_corners=False: src = (p + 0.5) ns / n - 0.5, clamped at 0 (ATen area_pixel_compute_source_index)
+        float src = (float(p) + 0.5f) * (float(ns) / float(n)) - 0.5f;
+        src = src < 0.f ? 0.f : src;
+        i0 = min(int(src), ns - 1);
+        i1 = i0 + (i0 < ns - 1 ? 1 : 0);
+        w1 = src - float(i0);
+        w0 = 1.0f - w1;
+    }
+}
+
+template <typename T> __device__ __forceinline__ float4 load4(const T *p);
+template <> __device__ __forceinline__ float4 load4<float>(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+template <> __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16 *p) {
+    const uint2 r = *reinterpret_cast<const uint2 *>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+template <> __device__ __forceinline__ float4 load4<__half>(const __half *p) {
+    const uint2 r = *reinterpret_cast<const uint2 *>(p);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&r.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T> __device__ __forceinline__ void store4(T *p, float4 v);
+template <> __device__ __forceinline__ void store4<float>(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16 *p, float4 v) {
+    uint2 r;
+    *reinterpret_cast<__nv_bfloat162 *>(&r.x) = __floats2bfloat162_rn(v.x, v.y);
+    *reinterpret_cast<__nv_bfloat162 *>(&r.y) = __floats2bfloat162_rn(v.z, v.w);
+    *reinterpret_cast<uint2 *>(p) = r;
+}
+template <> __device__ __forceinline__ void store4<__half>(__half *p, float4 v) {
+    uint2 r;
+    *reinterpret_cast<__half2 *>(&r.x) = __floats2half2_rn(v.x, v.y);
+    *reinterpret_cast<__half2 *>(&r.y) = __floats2half2_rn(v.z, v.w);
+    *reinterpret_cast<uint2 *>(p) = r;
+}
+
+struct TapTable {
+    int *i0, *i1;
+    float *w0, *w1;
+    __device__ void carve(float *&p, int n) {
+        i0 = reinterpret_cast<int *>(p);
+        i1 = i0 + n;
+        w0 = p + 2 * n;
+        w1 = p + 3 * n;
+        p += 4 * n;
+    }
+    __device__ void fill(int mode, int n, int ns) {
+        for (int p = threadIdx.x; p < n; p += kRsThreads) taps(mode, p, n, ns, i0[p], i1[p], w0[p], w1[p]);
+    }
+    // an index at the border has both bilinear taps on one cell: the two weights add up
+    __device__ __forceinline__ float weight(int p, int j) const { return (i0[p] == j ? w0[p] : 0.f) + (i1[p] == j ? w1[p] : 0.f); }
+};
+
+// small[i, j] = sum Wy[i, y] Wx[j, x] big[y, x]; one CTA per image.  General widths: row tiles staged in shared memory.
+template <typename T>
+__global__ void __launch_bounds__(kRsThreads)
+    resample_reduce_kernel(const T *__restrict__ big, T *__restrict__ small, int H, int W, int hs, int ws, int mode) {
+    extern __shared__ float sm[];
+    float *p = sm;
+    TapTable tx, ty;
+    tx.carve(p, W);
+    ty.carve(p, H);
+    int *xlo = reinterpret_cast<int *>(p);  // support [xlo[j], xhi[j]] of column bin j
+    int *xhi = xlo + ws;
+    p += 2 * ws;
+    float *acc = p;        // [hs][ws]
+    p += hs * ws;
+    float *Tr = p;         // [kRsRows][ws]
+    p += kRsRows * ws;
+    p = sm + (((p - sm) + 3) & ~3);  // 16-byte aligned tile rows
+    const int WP = ((W + 3) & ~3) + 4;
+    float *tile = p;       // [kRsRows][WP]
+    const int tid = threadIdx.x;
+    const T *img = big + int64_t(blockIdx.x) * H * W;
+
+    tx.fill(mode, W, ws);
+    ty.fill(mode, H, hs);
+    for (int i = tid; i < hs * ws; i += kRsThreads) acc[i] = 0.f;
+    __syncthreads();
+    for (int j = tid; j < ws; j += kRsThreads) {
+        int lo = W, hi = -1;
+        for (int x = 0; x < W; ++x)
+            if (tx.i0[x] == j || tx.i1[x] == j) {
+                lo = min(lo, x);
+                hi = max(hi, x);
+            }
+        xlo[j] = lo;
+        xhi[j] = hi;
+    }
+    for (int y0 = 0; y0 < H; y0 += kRsRows) {
+        const int nr = min(kRsRows, H - y0);
+        const T *src = img + int64_t(y0) * W;
+        if ((W & 3) == 0) {  // images start 4-element aligned whenever W % 4 == 0
+            const int W4 = W >> 2;
+            for (int i = tid; i < nr * W4; i += kRsThreads)
+                *reinterpret_cast<float4 *>(tile + (i / W4) * WP + 4 * (i % W4)) = load4<T>(src + 4 * i);
+        } else {
+            for (int i = tid; i < nr * W; i += kRsThreads) tile[(i / W) * WP + i % W] = to_f32<T>(src[i]);
+        }
+        __syncthreads();
+        for (int i = tid; i < nr * ws; i += kRsThreads) {
+            const int r = i / ws, j = i % ws;
+            float s = 0.f;
+            for (int x = xlo[j]; x <= xhi[j]; ++x) s = fmaf(tx.weight(x, j), tile[r * WP + x], s);
+            Tr[r * ws + j] = s;
+        }
+        __syncthreads();
+        for (int i = tid; i < hs * ws; i += kRsThreads) {
+            const int a = i / ws, j = i % ws;
+            float s = acc[i];
+            for (int r = 0; r < nr; ++r) s = fmaf(ty.weight(y0 + r, a), Tr[r * ws + j], s);
+            acc[i] = s;
+        }
+        // the next tile's loads do not touch Tr / acc; its first barrier orders them against this tile's readers
+    }
+    __syncthreads();
+    T *dst = small + int64_t(blockIdx.x) * hs * ws;
+    for (int i = tid; i < hs * ws; i += kRsThreads) dst[i] = from_f32<T>(acc[i]);
+}
+
+// Same map for W % 4 == 0, W <= 1024: vertical pass first, in registers.  Thread (rg, q) owns the four columns 4q..4q+3
+// of the row range rg and walks down them with 16-byte loads; the anchor rows a row touches are i0(y) <= i1(y) <=
+// i0(y) + 1 and never decrease, so two running sums per column suffice, flushed to Vp[rg][a][x] when i0 advances.
+// Then V = sum_rg Vp and the horizontal taps, four threads per output cell.
+constexpr int kRsUnroll = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(kRsThreads)
+    resample_reduce_rows_kernel(const T *__restrict__ big, T *__restrict__ small, int H, int W, int hs, int ws, int mode,
+                                int RG) {
+    extern __shared__ float sm[];
+    float *p = sm;
+    TapTable tx, ty;
+    tx.carve(p, W);
+    ty.carve(p, H);
+    int *xlo = reinterpret_cast<int *>(p);
+    int *xhi = xlo + ws;
+    p += 2 * ws;
+    p = sm + (((p - sm) + 3) & ~3);
+    float *Vp = p;  // [RG][hs][W]; slice 0 ends up holding the sum over rg
+    const int tid = threadIdx.x, W4 = W >> 2;
+    const T *img = big + int64_t(blockIdx.x) * H * W;
+
+    tx.fill(mode, W, ws);
+    ty.fill(mode, H, hs);
+    for (int i = tid; i < RG * hs * W; i += kRsThreads) Vp[i] = 0.f;
+    for (int j = tid; j < ws; j += kRsThreads) xlo[j] = W, xhi[j] = -1;
+    __syncthreads();
+    for (int x = tid; x < W; x += kRsThreads) {
+        atomicMin(xlo + tx.i0[x], x), atomicMax(xhi + tx.i0[x], x);
+        atomicMin(xlo + tx.i1[x], x), atomicMax(xhi + tx.i1[x], x);
+    }
+    if (tid < RG * W4) {
+        const int rg = tid / W4, q = tid % W4;
+        const int ya = int(int64_t(rg) * H / RG), yb = int(int64_t(rg + 1) * H / RG);
+        float *vp = Vp + int64_t(rg) * hs * W + 4 * q;
+        auto flush = [&](int a, const float4 &v) {
+            if (a >= 0 && a < hs) {
+                float4 *d = reinterpret_cast<float4 *>(vp + a * W);
+                float4 o = *d;
+                o.x += v.x, o.y += v.y, o.z += v.z, o.w += v.w;
+                *d = o;
+            }
+        };
+        auto axpy = [](float4 &acc, float w, const float4 &v) {
+            acc.x = fmaf(w, v.x, acc.x), acc.y = fmaf(w, v.y, acc.y), acc.z = fmaf(w, v.z, acc.z), acc.w = fmaf(w, v.w, acc.w);
+        };
+        int cur = -1;
+        float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+        const float4 zero = lo;
+        for (int y = ya; y < yb; y += kRsUnroll) {
+            float4 v[kRsUnroll];
+#pragma unroll
+            for (int u = 0; u < kRsUnroll; ++u)
+                if (y + u < yb) v[u] = load4<T>(img + int64_t(y + u) * W + 4 * q);
+#pragma unroll
+            for (int u = 0; u < kRsUnroll; ++u) {
+                if (y + u >= yb) break;
+                const int i0 = ty.i0[y + u], i1 = ty.i1[y + u];
+                if (i0 != cur) {  // warp-uniform: depends on the row only
+                    flush(cur, lo);
+                    if (i0 == cur + 1) {
+                        lo = hi;
+                    } else {
+                        flush(cur + 1, hi);
+                        lo = zero;
+                    }
+                    hi = zero;
+                    cur = i0;
+                }
+                axpy(lo, ty.w0[y + u], v[u]);
+                if (i1 == i0) axpy(lo, ty.w1[y + u], v[u]);
+                else axpy(hi, ty.w1[y + u], v[u]);
+            }
+        }
+        flush(cur, lo);
+        flush(cur + 1, hi);
+    }
+    __syncthreads();
+    for (int i = tid; i < hs * W; i += kRsThreads) {
+        float sacc = Vp[i];
+        for (int rg = 1; rg < RG; ++rg) sacc += Vp[int64_t(rg) * hs * W + i];
+        Vp[i] = sacc;
+    }
+    __syncthreads();
+    T *dst = small + int64_t(blockIdx.x) * hs * ws;
+    for (int c0 = 0; c0 < hs * ws; c0 += kRsThreads / 4) {
+        const int cell = c0 + tid / 4, part = tid % 4;
+        float sacc = 0.f;
+        int a = 0, j = 0;
+        if (cell < hs * ws) {
+            a = cell / ws, j = cell % ws;
+            for (int x = xlo[j] + part; x <= xhi[j]; x += 4) sacc = fmaf(tx.weight(x, j), Vp[a * W + x], sacc);
+        }
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+        if (cell < hs * ws && part == 0) dst[a * ws + j] = from_f32<T>(sacc);
+    }
+}
+
+// big[y, x] = sum Wy[i, y] Wx[j, x] small[i, j]; one CTA per image: horizontal pass into shared memory, then rows.
+template <typename T>
+__global__ void __launch_bounds__(kRsThreads)
+    resample_expand_kernel(const T *__restrict__ small, T *__restrict__ big, int H, int W, int hs, int ws, int mode) {
+    extern __shared__ float sm[];
+    float *p = sm;
+    TapTable tx, ty;
+    tx.carve(p, W);
+    ty.carve(p, H);
+    float *s = p;   // [hs][ws]
+    p += hs * ws;
+    p = sm + (((p - sm) + 3) & ~3);
+    float *hx = p;  // [hs][W]: rows of the small grid expanded along x
+    const int tid = threadIdx.x;
+    const T *src = small + int64_t(blockIdx.x) * hs * ws;
+    T *img = big + int64_t(blockIdx.x) * H * W;
+
+    tx.fill(mode, W, ws);
+    ty.fill(mode, H, hs);
+    for (int i = tid; i < hs * ws; i += kRsThreads) s[i] = to_f32<T>(src[i]);
+    __syncthreads();
+    for (int i = tid; i < hs * W; i += kRsThreads) {
+        const int a = i / W, x = i % W;
+        hx[i] = tx.w0[x] * s[a * ws + tx.i0[x]] + tx.w1[x] * s[a * ws + tx.i1[x]];
+    }
+    __syncthreads();
+    if ((W & 3) == 0 && (W >> 2) <= kRsThreads) {
+        // thread (rg, q) owns columns 4q..4q+3 of a row range; the two anchor rows stay in registers while i0(y) holds
+        const int W4 = W >> 2, RG = min(kRsThreads / W4, H);
+        if (tid < RG * W4) {
+            const int rg = tid / W4, q = tid % W4;
+            const int ya = int(int64_t(rg) * H / RG), yb = int(int64_t(rg + 1) * H / RG);
+            int c0 = -1, c1 = -1;
+            float4 u = make_float4(0.f, 0.f, 0.f, 0.f), v = u;
+            for (int y = ya; y < yb; ++y) {
+                const int i0 = ty.i0[y], i1 = ty.i1[y];
+                if (i0 != c0 || i1 != c1) {
+                    u = *reinterpret_cast<const float4 *>(hx + i0 * W + 4 * q);
+                    v = *reinterpret_cast<const float4 *>(hx + i1 * W + 4 * q);
+                    c0 = i0, c1 = i1;
+                }
+                const float a = ty.w0[y], b = ty.w1[y];
+                store4<T>(img + int64_t(y) * W + 4 * q,
+                          make_float4(a * u.x + b * v.x, a * u.y + b * v.y, a * u.z + b * v.z, a * u.w + b * v.w));
+            }
+        }
+    } else {
+        for (int i = tid; i < H * W; i += kRsThreads) {
+            const int y = i / W, x = i % W;
+            img[i] = from_f32<T>(ty.w0[y] * hx[ty.i0[y] * W + x] + ty.w1[y] * hx[ty.i1[y] * W + x]);
+        }
+    }
+}
+
+static int check_resample(const char *fn, int BC, int H, int W, int hs, int ws, int mode) {
+    if (BC < 1 || H < 1 || W < 1 || hs < 1 || ws < 1) { set_error("%s: sizes must be positive", fn); return MMI_ERR_ARG; }
+    if (H > kRsMaxBig || W > kRsMaxBig || hs * ws > kRsMaxSmall) {
+        set_error("%s: map up to %dx%d and anchor grid up to %d cells supported (got %dx%d, %dx%d)", fn, kRsMaxBig, kRsMaxBig,
+                  kRsMaxSmall, H, W, hs, ws);
+        return MMI_ERR_UNSUPPORTED;
+    }
+    if (mode == RS_POOL && (H < hs || W < ws)) {
+        set_error("%s: adaptive pooling needs the map (%dx%d) at least as large as the anchor grid (%dx%d)", fn, H, W, hs, ws);
+        return MMI_ERR_UNSUPPORTED;
+    }
+    return MMI_OK;
+}
+
+template <typename K>
+static int opt_in_smem(K kern, size_t smem) {
+    if (smem <= 48 * 1024) return MMI_OK;
+    return check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)), "resample smem attribute");
+}
+
+int resample_reduce_launch(const void *big, void *small, int BC, int H, int W, int hs, int ws, int mode, int dtype,
+                           cudaStream_t st, const char *fn) {
+    if (int e = check_resample(fn, BC, H, W, hs, ws, mode)) return e;
+    const int W4 = W >> 2;
+    int RG = W4 > 0 ? kRsThreads / W4 : 0;
+    RG = RG > H ? H : RG;
+    const size_t smem_rows = (size_t(4) * (H + W) + 2 * ws + 4 + size_t(RG) * hs * W) * sizeof(float);
+    const bool rows = (W & 3) == 0 && RG >= 1 && smem_rows <= 160 * 1024;
+    const size_t smem = rows ? smem_rows
+                             : (size_t(4) * (H + W) + 2 * ws + hs * ws + kRsRows * ws + 4 + size_t(kRsRows) * (((W + 3) & ~3) + 4)) * sizeof(float);
+#define MMI_RS_REDUCE(T)                                                                                                \
+    do {                                                                                                                \
+        if (rows) {                                                                                                     \
+            auto kern = resample_reduce_rows_kernel<T>;                                                                 \
+            if (int e = opt_in_smem(kern, smem)) return e;                                                              \
+            kern<<<BC, kRsThreads, smem, st>>>(static_cast<const T *>(big), static_cast<T *>(small), H, W, hs, ws, mode, RG); \
+        } else {                                                                                                        \
+            auto kern = resample_reduce_kernel<T>;                                                                      \
+            if (int e = opt_in_smem(kern, smem)) return e;                                                              \
+            kern<<<BC, kRsThreads, smem, st>>>(static_cast<const T *>(big), static_cast<T *>(small), H, W, hs, ws, mode); \
+        }                                                                                                               \
+    } while (0)
+    switch (dtype) {
+        case MMI_F32: MMI_RS_REDUCE(float); break;
+        case MMI_BF16: MMI_RS_REDUCE(__nv_bfloat16); break;
+        case MMI_F16: MMI_RS_REDUCE(__half); break;
+        default: set_error("%s: unknown dtype %d", fn, dtype); return MMI_ERR_ARG;
+    }
+#undef MMI_RS_REDUCE
+    return check_cuda(cudaGetLastError(), fn);
+}
+
+int resample_expand_launch(const void *small, void *big, int BC, int H, int W, int hs, int ws, int mode, int dtype,
+                           cudaStream_t st, const char *fn) {
+    if (int e = check_resample(fn, BC, H, W, hs, ws, mode)) return e;
+    const size_t smem = (size_t(4) * (H + W) + hs * ws + 4 + size_t(hs) * W) * sizeof(float);
+    if (smem > 200 * 1024) { set_error("%s: anchor rows x map width too large for shared memory (%d x %d)", fn, hs, W); return MMI_ERR_UNSUPPORTED; }
+#define MMI_RS_EXPAND(T)                                                                                                \
+    do {                                                                                                                \
+        auto kern = resample_expand_kernel<T>;                                                                          \
+        if (int e = opt_in_smem(kern, smem)) return e;                                                                  \
+        kern<<<BC, kRsThreads, smem, st>>>(static_cast<const T *>(small), static_cast<T *>(big), H, W, hs, ws, mode);   \
+    } while (0)
+    switch (dtype) {
+        case MMI_F32: MMI_RS_EXPAND(float); break;
+        case MMI_BF16: MMI_RS_EXPAND(__nv_bfloat16); break;
+        case MMI_F16: MMI_RS_EXPAND(__half); break;
+        default: set_error("%s: unknown dtype %d", fn, dtype); return MMI_ERR_ARG;
+    }
+#undef MMI_RS_EXPAND
+    return check_cuda(cudaGetLastError(), fn);
+}
+
+}  // namespace mmi

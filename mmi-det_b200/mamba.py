@@ -216,7 +216,8 @@ def install(ref_models=None, scan=True, pscan=True, ffm=True, fusion=False):
 
     scan    MambaBlock.selective_scan / selective_scan_seq  -> fused kernel (class attribute patch; ctor untouched)
     pscan   models.mamba.pscan (= PScan.apply)               -> mmidet_b200.pscan.pscan
-    ffm     models.common.extract_frequency2, Seperation_loss -> mmidet_b200.ffm
+    ffm     models.common.extract_frequency2, Seperation_loss -> mmidet_b200.ffm; GPT1_fourier.forward -> ffm.fourier_forward
+            (class attribute patch: the module keeps its ctor, parameters and state_dict)
     fusion  models.yolo_test.GPT                              -> MambaFusion (YAML rows naming GPT then build it)
     Returns the list of replaced attributes so a caller can restore them."""
     import importlib
@@ -244,6 +245,8 @@ def install(ref_models=None, scan=True, pscan=True, ffm=True, fusion=False):
         mc = mod("models.common")
         swap(mc, "extract_frequency2", _ffm.extract_frequency2)
         swap(mc, "Seperation_loss", _ffm.separation_loss)
+        if hasattr(mc, "GPT1_fourier"):
+            swap(mc.GPT1_fourier, "forward", _ffm.fourier_forward)
     if fusion:
         swap(mod("models.yolo_test"), "GPT", MambaFusion)
     return saved

@@ -273,3 +273,54 @@ def tokens_scatter(tok, shape):
     """Inverse of tokens_gather: tokens (B, 2*H*W, C) -> (rgb, ir) of `shape` = (B, C, H, W) (models/common.py:1352-1366)."""
     _require_cuda(tok, "tokens_scatter")
     return _TokensScatter.apply(tok, tuple(shape))
+
+
+def _resample(fn, src, out_shape, src_is_big):
+    """the four entry points share one signature: (src, dst, B*C, H, W, hs, ws) with (H, W) the map, (hs, ws) the anchors"""
+    global launches
+    lib = _lib.load()
+    src = src.contiguous()
+    dst = torch.empty(out_shape, dtype=src.dtype, device=src.device)
+    big, small = (src, dst) if src_is_big else (dst, src)
+    _lib.check(getattr(lib, fn)(_ptr(src), _ptr(dst), src.shape[0] * src.shape[1], big.shape[2], big.shape[3], small.shape[2],
+                                small.shape[3], _DT[src.dtype], _stream(src)), fn)
+    launches += 1
+    return dst
+
+
+class _AvgPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, size):
+        ctx.shape = x.shape
+        return _resample("mmi_avgpool_fwd", x, (*x.shape[:2], *size), True)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return _resample("mmi_avgpool_bwd", dy, ctx.shape, False), None
+
+
+class _UpsampleBilinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, size):
+        ctx.shape = x.shape
+        return _resample("mmi_upsample_bilinear_fwd", x, (*x.shape[:2], *size), False)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return _resample("mmi_upsample_bilinear_bwd", dy, ctx.shape, True), None
+
+
+def adaptive_avg_pool(x, size):
+    """nn.AdaptiveAvgPool2d(size) of models/common.py:324-325 on (B, C, H, W); one pass over the map per direction."""
+    _require_cuda(x, "adaptive_avg_pool")
+    if x.dtype not in _DT:
+        x = x.float()
+    return _AvgPool.apply(x, tuple(int(v) for v in size))
+
+
+def upsample_bilinear(x, size):
+    """F.interpolate(x, size=size, mode='bilinear') (align_corners=False) of models/common.py:540-543."""
+    _require_cuda(x, "upsample_bilinear")
+    if x.dtype not in _DT:
+        x = x.float()
+    return _UpsampleBilinear.apply(x, tuple(int(v) for v in size))

@@ -361,6 +361,29 @@ def separation_loss(M):
 
 # ----------------------------------------------------------------------------------------------
 # depthwise causal conv1d + SiLU on channels-last tokens (models/mamba.py:176-180 with nn.Conv1d of :125-128)
+def ffm_pattern(pool_vis, pool_ir, conv1_w, conv2_w):
+    """models/common.py:434-516 (GPT1_fourier.forward between avgpool and the transformer), literally:
+    pooled maps (B, C, h, w), conv1_w (8, C), conv2_w (C, 8) -> (token_embeddings (B, 2hw, C), pattenLoss).
+    1x1 convolutions are einsums over the channel axis; `.view(-1, h*w)` flattens (b, j) row-major."""
+    B, Cc, h, w = pool_vis.shape
+    sig = lambda v: 1.0 / (1.0 + np.exp(-v))  # noqa: E731
+    conv1 = lambda t: np.einsum("jc,bchw->bjhw", conv1_w.astype(np.float64), t.astype(np.float64))  # noqa: E731
+    rows_high, rows, toks = [], [], []
+    for fea in (pool_vis, pool_ir):
+        _, high = extract_frequency2(fea)                                   # :434-435
+        high_multi = high.astype(np.float32) * fea                          # :440-441 (fp16 * fp32 -> fp32)
+        rows_high.append(sig(conv1(high_multi)).reshape(-1, h * w))         # :444-455
+        M = sig(conv1(fea))                                                 # :476-480
+        rows.append(M.reshape(-1, h * w))                                   # :482-483
+        PT = np.einsum("cj,bjhw->bchw", conv2_w.astype(np.float64), M)      # :496-497
+        toks.append((PT * fea).reshape(B, Cc, -1))                          # :499-503
+    n_half = len(rows_high[0]) // 8                                         # :487
+    cat = np.concatenate([rows[0], rows[1], rows_high[0][:n_half], rows_high[1][:n_half]], axis=0)  # :488-489
+    loss = separation_loss(cat)                                             # :494
+    tok = np.concatenate(toks, axis=2).transpose(0, 2, 1)                   # :514-519
+    return np.ascontiguousarray(tok), loss
+
+
 def causal_conv1d_silu(x, w, bias=None, silu=True, dtype=np.float64):
     """x (B, L, ED); w (ED, K) [= conv1d.weight[:, 0, :]]; pre[t] = bias + sum_j w[:, j] * x[t-(K-1)+j]; y = silu(pre)."""
     x = np.asarray(x, dtype)

@@ -181,8 +181,38 @@ def gen_detector():
     save("detector_fusion", **arrs)
 
 
+def gen_pattern():
+    """GPT1_fourier.forward (common.py:357-552) with the transformer stack emptied (n_layer=0: pooling, Fourier split,
+    pattern maps, Seperation_loss, conv2 * fea, tokens, pos_emb, ln_f, upsample remain) -- outputs, the token
+    embeddings entering self.drop, and gradients of a seeded linear functional of the two output maps."""
+    for name, (B, Cc, H, W, seed) in {"pattern_b2": (2, 64, 12, 10, 0), "pattern_b9": (9, 16, 9, 11, 1)}.items():
+        torch.manual_seed(seed)
+        m = C.GPT1_fourier(Cc, n_layer=0).eval()
+        with torch.no_grad():
+            m.pos_emb.normal_(0, 0.5)
+            m.ln_f.weight.uniform_(0.5, 1.5)
+            m.ln_f.bias.normal_(0, 0.1)
+            m.conv1.weight.mul_(4.0)  # spread the sigmoids away from 0.5
+        g = torch.Generator().manual_seed(100 + seed)
+        vis = torch.randn(B, Cc, H, W, generator=g).requires_grad_()
+        ir = (torch.randn(B, Cc, H, W, generator=g) * 0.7 + 0.2).requires_grad_()
+        g1, g2 = torch.randn(B, Cc, H, W, generator=g), torch.randn(B, Cc, H, W, generator=g)
+        cap = {}
+        hk = m.drop.register_forward_pre_hook(lambda mod, inp: cap.__setitem__("drop_in", inp[0].detach().clone()))
+        pooled = []
+        hp = m.avgpool.register_forward_hook(lambda mod, inp, out: pooled.append(out.detach().clone()))
+        ro, io, loss = m([vis, ir])
+        hk.remove(), hp.remove()
+        ((ro * g1).sum() + (io * g2).sum()).backward()
+        print(name, "loss", float(loss), "rows", 18 * B)
+        save(name, vis=vis, ir=ir, g1=g1, g2=g2, conv1_w=m.conv1.weight, conv2_w=m.conv2.weight, pos_emb=m.pos_emb,
+             ln_w=m.ln_f.weight, ln_b=m.ln_f.bias, pool_vis=pooled[0], pool_ir=pooled[1], drop_in=cap["drop_in"],
+             rgb_out=ro, ir_out=io, loss=loss.detach().reshape(1), d_vis=vis.grad, d_ir=ir.grad,
+             d_conv1=m.conv1.weight.grad, d_conv2=m.conv2.weight.grad, d_pos=m.pos_emb.grad)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
-    todo = sys.argv[1:] or ["pscan", "selscan", "block", "ffm", "fusion", "detector"]
+    todo = sys.argv[1:] or ["pscan", "selscan", "block", "ffm", "fusion", "detector", "pattern"]
     for name in todo:
         globals()["gen_" + name]()

@@ -13,8 +13,12 @@ def _fake_tree():
         def selective_scan_seq(self, *a):
             return "ref_seq"
 
+    class GPT1_fourier:  # models/common.py:300
+        def forward(self, x):
+            return "ref_fourier"
+
     mamba = types.SimpleNamespace(MambaBlock=MambaBlock, pscan="ref_pscan")
-    common = types.SimpleNamespace(extract_frequency2="ref_ffm", Seperation_loss="ref_sep")
+    common = types.SimpleNamespace(extract_frequency2="ref_ffm", Seperation_loss="ref_sep", GPT1_fourier=GPT1_fourier)
     yolo = types.SimpleNamespace(GPT="ref_gpt")
     return types.SimpleNamespace(mamba=mamba, common=common, yolo_test=yolo)
 
@@ -26,6 +30,7 @@ def test_install_and_uninstall():
     assert t.mamba.pscan is pscan.pscan
     assert t.common.extract_frequency2 is ffm.extract_frequency2
     assert t.common.Seperation_loss is ffm.separation_loss
+    assert t.common.GPT1_fourier.forward is ffm.fourier_forward
     assert t.yolo_test.GPT is M.MambaFusion
     assert t.mamba.MambaBlock.selective_scan is t.mamba.MambaBlock.selective_scan_seq
     # the patched method is the fused operator: CPU tensors must raise, never fall back
@@ -38,6 +43,7 @@ def test_install_and_uninstall():
     M.uninstall(saved)
     assert t.mamba.pscan == "ref_pscan" and t.yolo_test.GPT == "ref_gpt" and t.common.extract_frequency2 == "ref_ffm"
     assert t.mamba.MambaBlock().selective_scan() == "ref_scan"
+    assert t.common.GPT1_fourier().forward(None) == "ref_fourier"
 
 
 def test_state_dict_layout_matches_reference(golden):

@@ -110,6 +110,16 @@ def test_separation_loss_matches_reference(golden):
     assert abs(O.separation_loss(g["M"]) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
 
 
+@pytest.mark.parametrize("tag", ["b2", "b9"])
+def test_ffm_pattern_matches_reference(golden, tag):
+    """pattern path of GPT1_fourier.forward (common.py:434-516) vs tensors captured inside the unmodified reference."""
+    g = golden(f"pattern_{tag}")
+    C = g["pool_vis"].shape[1]
+    tok, loss = O.ffm_pattern(g["pool_vis"], g["pool_ir"], g["conv1_w"].reshape(8, C), g["conv2_w"].reshape(C, 8))
+    assert relerr(tok + g["pos_emb"], g["drop_in"]) <= 1e-5
+    assert abs(loss - float(g["loss"][0])) <= 1e-5 * abs(float(g["loss"][0]))
+
+
 def test_causal_conv_oracle_matches_torch_conv1d():
     """the oracle's conv restatement vs the exact torch ops of models/mamba.py:176-180 (Conv1d padding=K-1, [:L], silu)."""
     import torch

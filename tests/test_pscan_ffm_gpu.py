@@ -91,3 +91,183 @@ def test_separation_loss(golden):
     assert abs(v - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
     M = np.random.default_rng(0).random((288, 64)).astype(np.float32)  # l = 18 * 16 (B=16), SURVEY 8a
     assert abs(float(separation_loss(_t(M))) - O.separation_loss(M)) <= 1e-4 * O.separation_loss(M)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# FFM pattern path (GPT1_fourier.forward between pooling and transformer, models/common.py:434-516)
+# ---------------------------------------------------------------------------------------------------------
+def _pattern_torch(vis, ir, w1, w2):
+    """plain torch restatement of the token path (differentiable, any dtype) used for gradient parity."""
+    toks = []
+    for fea in (vis, ir):
+        M = torch.sigmoid(torch.einsum("jc,bchw->bjhw", w1, fea))
+        toks.append((torch.einsum("cj,bjhw->bchw", w2, M) * fea).flatten(2))
+    return torch.cat(toks, dim=2).transpose(1, 2)
+
+
+@pytest.mark.parametrize("tag", ["b2", "b9"])
+def test_pattern_tokens_vs_reference_golden(golden, tag):
+    """tokens entering self.drop and pattenLoss captured inside the unmodified GPT1_fourier.forward."""
+    from mmidet_b200.ffm import pattern_tokens
+    g = golden(f"pattern_{tag}")
+    tok, loss = pattern_tokens(_t(g["pool_vis"]), _t(g["pool_ir"]), _t(g["conv1_w"]), _t(g["conv2_w"]))
+    assert tok.shape == g["drop_in"].shape and loss.dim() == 0 and not loss.requires_grad
+    assert relerr(tok.cpu().numpy() + g["pos_emb"], g["drop_in"]) <= 1e-5
+    assert abs(float(loss) - float(g["loss"][0])) <= 1e-5 * abs(float(g["loss"][0]))
+
+
+class _FourierStandIn(torch.nn.Module):
+    """Attribute-for-attribute stand-in for GPT1_fourier(d_model, n_layer=0) (models/common.py:300-343): the
+    reference class does not travel to the GPU box, fourier_forward only touches these members."""
+
+    def __init__(self, g):
+        super().__init__()
+        C = g["conv1_w"].shape[1]
+        self.n_embd, self.vert_anchors, self.horz_anchors = C, 8, 8
+        self.pos_emb = torch.nn.Parameter(torch.from_numpy(g["pos_emb"]))
+        self.trans_blocks = torch.nn.Sequential()
+        self.ln_f = torch.nn.LayerNorm(C)
+        self.drop = torch.nn.Dropout(0.1)
+        self.avgpool = torch.nn.AdaptiveAvgPool2d((8, 8))
+        self.conv1 = torch.nn.Conv2d(C, 8, kernel_size=1, bias=False)
+        self.conv2 = torch.nn.Conv2d(8, C, kernel_size=1, bias=False)
+        with torch.no_grad():
+            self.ln_f.weight.copy_(torch.from_numpy(g["ln_w"]))
+            self.ln_f.bias.copy_(torch.from_numpy(g["ln_b"]))
+            self.conv1.weight.copy_(torch.from_numpy(g["conv1_w"]))
+            self.conv2.weight.copy_(torch.from_numpy(g["conv2_w"]))
+
+
+@pytest.mark.parametrize("tag", ["b2", "b9"])
+def test_fourier_forward_vs_reference_golden(golden, tag):
+    """the replacement bound onto GPT1_fourier.forward: both output maps, the loss and the gradients of a seeded
+    functional of the outputs w.r.t. both inputs, conv1, conv2 and pos_emb -- all from the unmodified reference."""
+    from mmidet_b200.ffm import fourier_forward
+    g = golden(f"pattern_{tag}")
+    m = _FourierStandIn(g).cuda().eval()
+    vis, ir = _t(g["vis"]).requires_grad_(True), _t(g["ir"]).requires_grad_(True)
+    ro, io, loss = fourier_forward(m, [vis, ir])
+    assert m.pattenLoss is loss
+    assert relerr(ro.detach().cpu().numpy(), g["rgb_out"]) <= 1e-4
+    assert relerr(io.detach().cpu().numpy(), g["ir_out"]) <= 1e-4
+    assert abs(float(loss) - float(g["loss"][0])) <= 1e-5 * abs(float(g["loss"][0]))
+    ((ro * _t(g["g1"])).sum() + (io * _t(g["g2"])).sum()).backward()
+    for got, key in ((vis.grad, "d_vis"), (ir.grad, "d_ir"), (m.conv1.weight.grad, "d_conv1"),
+                     (m.conv2.weight.grad, "d_conv2"), (m.pos_emb.grad, "d_pos")):
+        assert relerr(got.cpu().numpy(), g[key]) <= 1e-4, key
+
+
+@pytest.mark.parametrize("B,C,hw", [(1, 8, (8, 8)), (3, 100, (4, 6)), (16, 256, (8, 8)), (2, 1024, (8, 16)), (17, 33, (5, 5))])
+def test_pattern_tokens_vs_oracle_and_autograd(B, C, hw):
+    """forward vs the numpy oracle, backward vs fp64 autograd of the same formula; ragged C, P and B > 8 (two
+    batch entries feed the high-pass rows)."""
+    from mmidet_b200.ffm import pattern_tokens
+    rng = np.random.default_rng(B * 1000 + C)
+    vis = rng.standard_normal((B, C, *hw)).astype(np.float32)
+    ir = (rng.standard_normal((B, C, *hw)) * 0.5 + 0.3).astype(np.float32)
+    w1 = (rng.standard_normal((8, C)) * 2.0 / np.sqrt(C)).astype(np.float32)
+    w2 = rng.standard_normal((C, 8)).astype(np.float32)
+    dtok = rng.standard_normal((B, 2 * hw[0] * hw[1], C)).astype(np.float32)
+    tv, ti = _t(vis).requires_grad_(True), _t(ir).requires_grad_(True)
+    t1, t2 = _t(w1.reshape(8, C, 1, 1)).requires_grad_(True), _t(w2.reshape(C, 8, 1, 1)).requires_grad_(True)
+    tok, loss = pattern_tokens(tv, ti, t1, t2)
+    otok, oloss = O.ffm_pattern(vis, ir, w1, w2)
+    assert relerr(tok.detach().cpu().numpy(), otok) <= 1e-5
+    assert abs(float(loss) - oloss) <= 1e-5 * abs(oloss)
+    grads = torch.autograd.grad(tok, (tv, ti, t1, t2), _t(dtok))
+    dv, di, d1, d2 = (torch.from_numpy(a).double().cuda().requires_grad_(True) for a in (vis, ir, w1, w2))
+    ref = torch.autograd.grad(_pattern_torch(dv, di, d1, d2), (dv, di, d1, d2), _t(dtok).double())
+    for got, want, name in zip(grads, ref, ("dvis", "dir", "dconv1", "dconv2")):
+        assert relerr(got.cpu().numpy().reshape(want.shape), want.cpu().numpy()) <= 1e-4, name
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_pattern_tokens_half_inputs(dtype):
+    """16-bit pooled maps (autocast): fp32 arithmetic inside, tokens and input gradients in the input dtype."""
+    from mmidet_b200.ffm import pattern_tokens
+    torch.manual_seed(3)
+    B, C = 4, 128
+    vis = torch.randn(B, C, 8, 8, device="cuda").to(dtype).requires_grad_(True)
+    ir = torch.randn(B, C, 8, 8, device="cuda").to(dtype).requires_grad_(True)
+    w1 = (torch.randn(8, C, 1, 1, device="cuda") * 0.2).requires_grad_(True)
+    w2 = torch.randn(C, 8, 1, 1, device="cuda").requires_grad_(True)
+    dtok = torch.randn(B, 128, C, device="cuda")
+    tok, loss = pattern_tokens(vis, ir, w1, w2)
+    assert tok.dtype == dtype
+    grads = torch.autograd.grad(tok, (vis, ir, w1, w2), dtok.to(dtype))
+    dv, di = vis.detach().double().requires_grad_(True), ir.detach().double().requires_grad_(True)
+    d1, d2 = w1.detach().double().reshape(8, C).requires_grad_(True), w2.detach().double().reshape(C, 8).requires_grad_(True)
+    rt = _pattern_torch(dv, di, d1, d2)
+    ref = torch.autograd.grad(rt, (dv, di, d1, d2), dtok.to(dtype).double())
+    assert relerr(tok.detach().float().cpu().numpy(), rt.detach().cpu().numpy()) <= 2e-2
+    otok, oloss = O.ffm_pattern(vis.detach().float().cpu().numpy(), ir.detach().float().cpu().numpy(),
+                                w1.detach().reshape(8, C).cpu().numpy(), w2.detach().reshape(C, 8).cpu().numpy())
+    assert abs(float(loss) - oloss) <= 1e-4 * abs(oloss)
+    for got, want in zip(grads, ref):
+        assert relerr(got.float().cpu().numpy().reshape(want.shape), want.cpu().numpy()) <= 2e-2
+
+
+def test_pattern_tokens_rejects_bad_input():
+    from mmidet_b200.ffm import pattern_tokens
+    with pytest.raises(RuntimeError):
+        pattern_tokens(torch.zeros(1, 8, 8, 8), torch.zeros(1, 8, 8, 8), torch.zeros(8, 8, 1, 1), torch.zeros(8, 8, 1, 1))
+    z = torch.zeros(1, 8, 12, 12, device="cuda")  # 144 pooled positions > 128
+    with pytest.raises(RuntimeError, match="vert_anchors"):
+        pattern_tokens(z, z, torch.zeros(8, 8, 1, 1, device="cuda"), torch.zeros(8, 8, 1, 1, device="cuda"))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# resampling either side of the FFM token path (models/common.py:324-325, :396-397, :540-543)
+# ---------------------------------------------------------------------------------------------------------
+_RESAMPLE_SHAPES = [((2, 3, 160, 160), (8, 8)), ((1, 5, 37, 53), (8, 8)), ((2, 4, 20, 24), (4, 6)), ((1, 2, 8, 8), (8, 8)),
+                    ((1, 3, 12, 10), (8, 8)), ((1, 1, 333, 64), (16, 16)), ((3, 2, 9, 11), (1, 1))]
+
+
+@pytest.mark.parametrize("shape,anchors", _RESAMPLE_SHAPES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_adaptive_avg_pool_matches_torch(shape, anchors, dtype):
+    """forward and backward vs nn.AdaptiveAvgPool2d (the op the reference calls), incl. overlapping ragged windows."""
+    import torch.nn.functional as F
+    from mmidet_b200 import ops
+    torch.manual_seed(1)
+    x = torch.randn(*shape, device="cuda").to(dtype).requires_grad_(True)
+    g = torch.randn(*shape[:2], *anchors, device="cuda").to(dtype)
+    y = ops.adaptive_avg_pool(x, anchors)
+    (dx,) = torch.autograd.grad(y, x, g)
+    xr = x.detach().double().requires_grad_(True)
+    yr = F.adaptive_avg_pool2d(xr, anchors)
+    (dxr,) = torch.autograd.grad(yr, xr, g.double())
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert y.dtype == dtype and dx.shape == x.shape
+    assert relerr(y.detach().float().cpu().numpy(), yr.detach().cpu().numpy()) <= tol
+    assert relerr(dx.float().cpu().numpy(), dxr.cpu().numpy()) <= tol
+
+
+@pytest.mark.parametrize("shape,anchors", _RESAMPLE_SHAPES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_upsample_bilinear_matches_torch(shape, anchors, dtype):
+    """forward and backward vs F.interpolate(mode='bilinear') with the default align_corners=False."""
+    import torch.nn.functional as F
+    from mmidet_b200 import ops
+    torch.manual_seed(2)
+    x = torch.randn(*shape[:2], *anchors, device="cuda").to(dtype).requires_grad_(True)
+    g = torch.randn(*shape, device="cuda").to(dtype)
+    y = ops.upsample_bilinear(x, shape[2:])
+    (dx,) = torch.autograd.grad(y, x, g)
+    xr = x.detach().double().requires_grad_(True)
+    yr = F.interpolate(xr, size=list(shape[2:]), mode="bilinear")
+    (dxr,) = torch.autograd.grad(yr, xr, g.double())
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert y.shape == tuple(shape) and y.dtype == dtype
+    assert relerr(y.detach().float().cpu().numpy(), yr.detach().cpu().numpy()) <= tol
+    assert relerr(dx.float().cpu().numpy(), dxr.cpu().numpy()) <= tol
+
+
+def test_resample_rejects_unsupported():
+    from mmidet_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.adaptive_avg_pool(torch.zeros(1, 1, 8, 8), (8, 8))
+    with pytest.raises(RuntimeError, match="at least as large"):
+        ops.adaptive_avg_pool(torch.zeros(1, 1, 4, 4, device="cuda"), (8, 8))
+    with pytest.raises(RuntimeError, match="anchor grid"):
+        ops.upsample_bilinear(torch.zeros(1, 1, 32, 32, device="cuda"), (64, 64))
