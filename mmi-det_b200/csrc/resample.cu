@@ -5,14 +5,16 @@
 // index touches at most two small-grid indices (a pooling window pair / the two bilinear taps):
 //     reduce:  small[i, j] = sum_{y, x} Wy[i, y] Wx[j, x] big[y, x]     (pool forward, upsample backward)
 //     expand:  big[y, x]   = sum_{i, j} Wy[i, y] Wx[j, x] small[i, j]   (upsample forward, pool backward)
-// so two kernels cover the four directions; each streams the big map through HBM exactly once (one CTA per (b, c)
-// image, fp32 accumulation, fixed summation order -- no atomics).  The stock backward of the bilinear upsample
+// so two kernels cover the four directions; each streams the big map through HBM exactly once (a CTA works on one
+// (b, c) image at a time, fp32 accumulation, fixed summation order -- no atomics).  The stock backward of the bilinear upsample
 // scatters 25600 gradients per image onto 64 addresses with global atomics (12 ms at B=16, C=128, 160x160 fp32 on
 // B200, profiles/r01_ffm_module.txt); the reduce kernel reads the gradient once.
 #include "../../include/mmidet_b200.h"
 #include "common.cuh"
 
 namespace mmi {
+
+int sm_count();
 
 constexpr int kRsThreads = 256;
 constexpr int kRsRows = 16;        // big-grid rows per tile in the reduce kernel
@@ -25,13 +27,15 @@ enum { RS_POOL = 0, RS_BILINEAR = 1 };
 __device__ __forceinline__ void taps(int mode, int p, int n, int ns, int &i0, int &i1, float &w0, float &w1) {
     if (mode == RS_POOL) {
         // adaptive windows [floor(j n / ns), ceil((j + 1) n / ns)): p lies in windows lo..hi, hi - lo <= 1 for n >= ns
-        const int lo = int((int64_t(p) * ns) / n), hi = int((int64_t(p + 1) * ns - 1) / n);
-        auto inv_len = [&](int j) {
-            const int s = int((int64_t(j) * n) / ns), e = int((int64_t(j + 1) * n + ns - 1) / ns);
+        // (32-bit arithmetic: n <= 2048 and ns <= 256 keep every product below 2^20)
+        const unsigned un = n, uns = ns, up = p;
+        const unsigned lo = (up * uns) / un, hi = ((up + 1) * uns - 1) / un;
+        auto inv_len = [&](unsigned j) {
+            const unsigned s = (j * un) / uns, e = ((j + 1) * un + uns - 1) / uns;
             return 1.0f / float(e - s);
         };
-        i0 = lo;
-        i1 = hi;
+        i0 = int(lo);
+        i1 = int(hi);
         w0 = inv_len(lo);
         w1 = hi != lo ? inv_len(hi) : 0.f;
     } else {
@@ -74,21 +78,31 @@ template <> __device__ __forceinline__ void store4<__half>(__half *p, float4 v) 
     *reinterpret_cast<uint2 *>(p) = r;
 }
 
+struct __align__(16) Tap {
+    int i0, i1;
+    float w0, w1;
+};
+
+// per-index taps in shared memory, one 16-byte entry each (a single broadcast load per row / column)
 struct TapTable {
-    int *i0, *i1;
-    float *w0, *w1;
+    Tap *t;
     __device__ void carve(float *&p, int n) {
-        i0 = reinterpret_cast<int *>(p);
-        i1 = i0 + n;
-        w0 = p + 2 * n;
-        w1 = p + 3 * n;
+        t = reinterpret_cast<Tap *>(p);
         p += 4 * n;
     }
     __device__ void fill(int mode, int n, int ns) {
-        for (int p = threadIdx.x; p < n; p += kRsThreads) taps(mode, p, n, ns, i0[p], i1[p], w0[p], w1[p]);
+        for (int p = threadIdx.x; p < n; p += kRsThreads) {
+            Tap e;
+            taps(mode, p, n, ns, e.i0, e.i1, e.w0, e.w1);
+            t[p] = e;
+        }
     }
+    __device__ __forceinline__ Tap at(int p) const { return t[p]; }
     // an index at the border has both bilinear taps on one cell: the two weights add up
-    __device__ __forceinline__ float weight(int p, int j) const { return (i0[p] == j ? w0[p] : 0.f) + (i1[p] == j ? w1[p] : 0.f); }
+    __device__ __forceinline__ float weight(int p, int j) const {
+        const Tap e = t[p];
+        return (e.i0 == j ? e.w0 : 0.f) + (e.i1 == j ? e.w1 : 0.f);
+    }
 };
 
 // small[i, j] = sum Wy[i, y] Wx[j, x] big[y, x]; one CTA per image.  General widths: row tiles staged in shared memory.
@@ -120,7 +134,7 @@ __global__ void __launch_bounds__(kRsThreads)
     for (int j = tid; j < ws; j += kRsThreads) {
         int lo = W, hi = -1;
         for (int x = 0; x < W; ++x)
-            if (tx.i0[x] == j || tx.i1[x] == j) {
+            if (tx.at(x).i0 == j || tx.at(x).i1 == j) {
                 lo = min(lo, x);
                 hi = max(hi, x);
             }
@@ -165,9 +179,9 @@ __global__ void __launch_bounds__(kRsThreads)
 constexpr int kRsUnroll = 8;
 
 template <typename T>
-__global__ void __launch_bounds__(kRsThreads)
-    resample_reduce_rows_kernel(const T *__restrict__ big, T *__restrict__ small, int H, int W, int hs, int ws, int mode,
-                                int RG) {
+__global__ void __launch_bounds__(kRsThreads, 3)
+    resample_reduce_rows_kernel(const T *__restrict__ big, T *__restrict__ small, int BC, int H, int W, int hs, int ws,
+                                int mode, int RG) {
     extern __shared__ float sm[];
     float *p = sm;
     TapTable tx, ty;
@@ -179,21 +193,29 @@ __global__ void __launch_bounds__(kRsThreads)
     p = sm + (((p - sm) + 3) & ~3);
     float *Vp = p;  // [RG][hs][W]; slice 0 ends up holding the sum over rg
     const int tid = threadIdx.x, W4 = W >> 2;
-    const T *img = big + int64_t(blockIdx.x) * H * W;
 
     tx.fill(mode, W, ws);
     ty.fill(mode, H, hs);
-    for (int i = tid; i < RG * hs * W; i += kRsThreads) Vp[i] = 0.f;
-    for (int j = tid; j < ws; j += kRsThreads) xlo[j] = W, xhi[j] = -1;
+    for (int j = tid; j < ws; j += kRsThreads) xlo[j] = 0, xhi[j] = -1;  // a bin no column touches stays empty
     __syncthreads();
+    // support [xlo[j], xhi[j]] of column bin j: the columns touching a bin are contiguous, so each end has one writer
     for (int x = tid; x < W; x += kRsThreads) {
-        atomicMin(xlo + tx.i0[x], x), atomicMax(xhi + tx.i0[x], x);
-        atomicMin(xlo + tx.i1[x], x), atomicMax(xhi + tx.i1[x], x);
+        const Tap e = tx.at(x);
+        const int bins[2] = {e.i0, e.i1};
+        for (int k = 0; k < 2; ++k) {
+            const int bn = bins[k];
+            if (x == 0 || (tx.at(x - 1).i0 != bn && tx.at(x - 1).i1 != bn)) xlo[bn] = x;
+            if (x == W - 1 || (tx.at(x + 1).i0 != bn && tx.at(x + 1).i1 != bn)) xhi[bn] = x;
+        }
     }
+    // tables are image-independent: a CTA builds them once and walks over images
+    for (int im = blockIdx.x; im < BC; im += gridDim.x) {
+    const T *img = big + int64_t(im) * H * W;
     if (tid < RG * W4) {
         const int rg = tid / W4, q = tid % W4;
-        const int ya = int(int64_t(rg) * H / RG), yb = int(int64_t(rg + 1) * H / RG);
+        const int ya = int(unsigned(rg) * unsigned(H) / unsigned(RG)), yb = int(unsigned(rg + 1) * unsigned(H) / unsigned(RG));
         float *vp = Vp + int64_t(rg) * hs * W + 4 * q;
+        for (int a = 0; a < hs; ++a) *reinterpret_cast<float4 *>(vp + a * W) = make_float4(0.f, 0.f, 0.f, 0.f);
         auto flush = [&](int a, const float4 &v) {
             if (a >= 0 && a < hs) {
                 float4 *d = reinterpret_cast<float4 *>(vp + a * W);
@@ -216,7 +238,8 @@ __global__ void __launch_bounds__(kRsThreads)
 #pragma unroll
             for (int u = 0; u < kRsUnroll; ++u) {
                 if (y + u >= yb) break;
-                const int i0 = ty.i0[y + u], i1 = ty.i1[y + u];
+                const Tap e = ty.at(y + u);
+                const int i0 = e.i0, i1 = e.i1;
                 if (i0 != cur) {  // warp-uniform: depends on the row only
                     flush(cur, lo);
                     if (i0 == cur + 1) {
@@ -228,22 +251,25 @@ __global__ void __launch_bounds__(kRsThreads)
                     hi = zero;
                     cur = i0;
                 }
-                axpy(lo, ty.w0[y + u], v[u]);
-                if (i1 == i0) axpy(lo, ty.w1[y + u], v[u]);
-                else axpy(hi, ty.w1[y + u], v[u]);
+                axpy(lo, e.w0, v[u]);
+                if (i1 == i0) axpy(lo, e.w1, v[u]);
+                else axpy(hi, e.w1, v[u]);
             }
         }
         flush(cur, lo);
         flush(cur + 1, hi);
     }
     __syncthreads();
-    for (int i = tid; i < hs * W; i += kRsThreads) {
-        float sacc = Vp[i];
-        for (int rg = 1; rg < RG; ++rg) sacc += Vp[int64_t(rg) * hs * W + i];
-        Vp[i] = sacc;
+    for (int i = tid; i < hs * W4; i += kRsThreads) {
+        float4 a = reinterpret_cast<const float4 *>(Vp)[i];
+        for (int rg = 1; rg < RG; ++rg) {
+            const float4 b = reinterpret_cast<const float4 *>(Vp + int64_t(rg) * hs * W)[i];
+            a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+        }
+        reinterpret_cast<float4 *>(Vp)[i] = a;
     }
     __syncthreads();
-    T *dst = small + int64_t(blockIdx.x) * hs * ws;
+    T *dst = small + int64_t(im) * hs * ws;
     for (int c0 = 0; c0 < hs * ws; c0 += kRsThreads / 4) {
         const int cell = c0 + tid / 4, part = tid % 4;
         float sacc = 0.f;
@@ -256,12 +282,14 @@ __global__ void __launch_bounds__(kRsThreads)
         sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
         if (cell < hs * ws && part == 0) dst[a * ws + j] = from_f32<T>(sacc);
     }
+    __syncthreads();  // slice 0 of Vp is re-zeroed by the next image
+    }
 }
 
 // big[y, x] = sum Wy[i, y] Wx[j, x] small[i, j]; one CTA per image: horizontal pass into shared memory, then rows.
 template <typename T>
 __global__ void __launch_bounds__(kRsThreads)
-    resample_expand_kernel(const T *__restrict__ small, T *__restrict__ big, int H, int W, int hs, int ws, int mode) {
+    resample_expand_kernel(const T *__restrict__ small, T *__restrict__ big, int BC, int H, int W, int hs, int ws, int mode) {
     extern __shared__ float sm[];
     float *p = sm;
     TapTable tx, ty;
@@ -272,16 +300,17 @@ __global__ void __launch_bounds__(kRsThreads)
     p = sm + (((p - sm) + 3) & ~3);
     float *hx = p;  // [hs][W]: rows of the small grid expanded along x
     const int tid = threadIdx.x;
-    const T *src = small + int64_t(blockIdx.x) * hs * ws;
-    T *img = big + int64_t(blockIdx.x) * H * W;
-
     tx.fill(mode, W, ws);
     ty.fill(mode, H, hs);
+    for (int im = blockIdx.x; im < BC; im += gridDim.x) {
+    const T *src = small + int64_t(im) * hs * ws;
+    T *img = big + int64_t(im) * H * W;
     for (int i = tid; i < hs * ws; i += kRsThreads) s[i] = to_f32<T>(src[i]);
     __syncthreads();
     for (int i = tid; i < hs * W; i += kRsThreads) {
         const int a = i / W, x = i % W;
-        hx[i] = tx.w0[x] * s[a * ws + tx.i0[x]] + tx.w1[x] * s[a * ws + tx.i1[x]];
+        const Tap e = tx.at(x);
+        hx[i] = e.w0 * s[a * ws + e.i0] + e.w1 * s[a * ws + e.i1];
     }
     __syncthreads();
     if ((W & 3) == 0 && (W >> 2) <= kRsThreads) {
@@ -289,26 +318,32 @@ __global__ void __launch_bounds__(kRsThreads)
         const int W4 = W >> 2, RG = min(kRsThreads / W4, H);
         if (tid < RG * W4) {
             const int rg = tid / W4, q = tid % W4;
-            const int ya = int(int64_t(rg) * H / RG), yb = int(int64_t(rg + 1) * H / RG);
+            const int ya = int(unsigned(rg) * unsigned(H) / unsigned(RG)), yb = int(unsigned(rg + 1) * unsigned(H) / unsigned(RG));
             int c0 = -1, c1 = -1;
             float4 u = make_float4(0.f, 0.f, 0.f, 0.f), v = u;
-            for (int y = ya; y < yb; ++y) {
-                const int i0 = ty.i0[y], i1 = ty.i1[y];
+            const float *hq = hx + 4 * q;
+            T *dst = img + int64_t(ya) * W + 4 * q;
+#pragma unroll 4
+            for (int y = ya; y < yb; ++y, dst += W) {
+                const Tap e = ty.at(y);
+                const int i0 = e.i0, i1 = e.i1;
                 if (i0 != c0 || i1 != c1) {
-                    u = *reinterpret_cast<const float4 *>(hx + i0 * W + 4 * q);
-                    v = *reinterpret_cast<const float4 *>(hx + i1 * W + 4 * q);
+                    u = *reinterpret_cast<const float4 *>(hq + i0 * W);
+                    v = *reinterpret_cast<const float4 *>(hq + i1 * W);
                     c0 = i0, c1 = i1;
                 }
-                const float a = ty.w0[y], b = ty.w1[y];
-                store4<T>(img + int64_t(y) * W + 4 * q,
-                          make_float4(a * u.x + b * v.x, a * u.y + b * v.y, a * u.z + b * v.z, a * u.w + b * v.w));
+                const float a = e.w0, b = e.w1;
+                store4<T>(dst, make_float4(a * u.x + b * v.x, a * u.y + b * v.y, a * u.z + b * v.z, a * u.w + b * v.w));
             }
         }
     } else {
         for (int i = tid; i < H * W; i += kRsThreads) {
             const int y = i / W, x = i % W;
-            img[i] = from_f32<T>(ty.w0[y] * hx[ty.i0[y] * W + x] + ty.w1[y] * hx[ty.i1[y] * W + x]);
+            const Tap e = ty.at(y);
+            img[i] = from_f32<T>(e.w0 * hx[e.i0 * W + x] + e.w1 * hx[e.i1 * W + x]);
         }
+    }
+    __syncthreads();  // s / hx are rewritten for the next image
     }
 }
 
@@ -328,8 +363,28 @@ static int check_resample(const char *fn, int BC, int H, int W, int hs, int ws, 
 
 template <typename K>
 static int opt_in_smem(K kern, size_t smem) {
-    if (smem <= 48 * 1024) return MMI_OK;
-    return check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)), "resample smem attribute");
+    // Streaming kernels with no L1 reuse: give the carve-out to shared memory so the CTA count is register-bound.
+    // Attributes are per device and sticky: set once per (kernel, device), and again only for a larger request.
+    struct Seen { const void *fn; int dev; size_t bytes; };
+    static thread_local Seen seen[32] = {};  // 2 kernels... x 3 dtypes x devices touched by this thread; overflow just re-sets
+    int dev = 0;
+    if (int e = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return e;
+    const void *fn = reinterpret_cast<const void *>(kern);
+    Seen *slot = &seen[0];
+    for (Seen &c : seen) {
+        if ((c.fn == fn && c.dev == dev) || c.fn == nullptr) { slot = &c; break; }
+    }
+    if (slot->fn != fn || slot->dev != dev) *slot = Seen{fn, dev, 0};
+    size_t &have = slot->bytes;
+    if (have == 0)
+        if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared),
+                               "resample carve-out attribute"))
+            return e;
+    if (smem > 48 * 1024 && smem > have)
+        if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)), "resample smem attribute"))
+            return e;
+    if (smem > have || have == 0) have = smem > 0 ? smem : 1;
+    return MMI_OK;
 }
 
 int resample_reduce_launch(const void *big, void *small, int BC, int H, int W, int hs, int ws, int mode, int dtype,
@@ -347,7 +402,7 @@ int resample_reduce_launch(const void *big, void *small, int BC, int H, int W, i
         if (rows) {                                                                                                     \
             auto kern = resample_reduce_rows_kernel<T>;                                                                 \
             if (int e = opt_in_smem(kern, smem)) return e;                                                              \
-            kern<<<BC, kRsThreads, smem, st>>>(static_cast<const T *>(big), static_cast<T *>(small), H, W, hs, ws, mode, RG); \
+            kern<<<min(BC, 3 * sm_count()), kRsThreads, smem, st>>>(static_cast<const T *>(big), static_cast<T *>(small), BC, H, W, hs, ws, mode, RG); \
         } else {                                                                                                        \
             auto kern = resample_reduce_kernel<T>;                                                                      \
             if (int e = opt_in_smem(kern, smem)) return e;                                                              \
@@ -373,7 +428,7 @@ int resample_expand_launch(const void *small, void *big, int BC, int H, int W, i
     do {                                                                                                                \
         auto kern = resample_expand_kernel<T>;                                                                          \
         if (int e = opt_in_smem(kern, smem)) return e;                                                                  \
-        kern<<<BC, kRsThreads, smem, st>>>(static_cast<const T *>(small), static_cast<T *>(big), H, W, hs, ws, mode);   \
+        kern<<<BC, kRsThreads, smem, st>>>(static_cast<const T *>(small), static_cast<T *>(big), BC, H, W, hs, ws, mode);  \
     } while (0)
     switch (dtype) {
         case MMI_F32: MMI_RS_EXPAND(float); break;
