@@ -271,3 +271,32 @@ def test_resample_rejects_unsupported():
         ops.adaptive_avg_pool(torch.zeros(1, 1, 4, 4, device="cuda"), (8, 8))
     with pytest.raises(RuntimeError, match="anchor grid"):
         ops.upsample_bilinear(torch.zeros(1, 1, 32, 32, device="cuda"), (64, 64))
+
+
+def test_fourier_forward_graph_replay(golden):
+    """batch-1 inference of the FFM forward replayed as a CUDA graph (graphs.Graphed) == eager, for fresh inputs too."""
+    from mmidet_b200.ffm import fourier_forward
+    from mmidet_b200.graphs import Graphed
+    g = golden("pattern_b2")
+    m = _FourierStandIn(g).cuda().eval()
+    C = m.n_embd
+    torch.manual_seed(5)
+    m.trans_blocks = torch.nn.Sequential(torch.nn.Linear(C, C), torch.nn.GELU(), torch.nn.Linear(C, C)).cuda()
+
+    class Wrap(torch.nn.Module):
+        def __init__(self, inner):
+            super().__init__()
+            self.inner = inner
+
+        def forward(self, x):
+            return fourier_forward(self.inner, x)
+
+    fast = Graphed(Wrap(m))
+    for seed in (0, 1, 2):
+        torch.manual_seed(seed)
+        vis, ir = torch.randn(1, C, 40, 40, device="cuda"), torch.randn(1, C, 40, 40, device="cuda")
+        with torch.no_grad():
+            want = fourier_forward(m, [vis, ir])
+        got = fast([vis, ir])
+        for a, b in zip(got, want):
+            assert torch.allclose(a, b, rtol=0, atol=0), seed
