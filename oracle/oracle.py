@@ -361,6 +361,40 @@ def separation_loss(M):
 
 # ----------------------------------------------------------------------------------------------
 # depthwise causal conv1d + SiLU on channels-last tokens (models/mamba.py:176-180 with nn.Conv1d of :125-128)
+def adaptive_avg_pool2d(x, size):
+    """nn.AdaptiveAvgPool2d(size) as GPT1_fourier uses it (models/common.py:324-325, :396-397): cell (i, j) averages
+    rows [floor(i H / hs), ceil((i + 1) H / hs)) and the matching columns (windows overlap when H % hs != 0)."""
+    x = np.asarray(x, np.float64)
+    H, W = x.shape[-2:]
+    hs, ws = size
+    out = np.empty(x.shape[:-2] + (hs, ws))
+    for i in range(hs):
+        r0, r1 = (i * H) // hs, -((-(i + 1) * H) // hs)
+        for j in range(ws):
+            c0, c1 = (j * W) // ws, -((-(j + 1) * W) // ws)
+            out[..., i, j] = x[..., r0:r1, c0:c1].mean(axis=(-2, -1))
+    return out
+
+
+def _bilinear_taps(n_out, n_in):
+    """align_corners=False source taps of F.interpolate(mode='bilinear') (models/common.py:540-543)."""
+    src = np.maximum((np.arange(n_out) + 0.5) * (n_in / n_out) - 0.5, 0.0)
+    i0 = np.minimum(src.astype(np.int64), n_in - 1)
+    i1 = np.minimum(i0 + 1, n_in - 1)
+    lam = src - i0
+    return i0, i1, lam
+
+
+def upsample_bilinear(x, size):
+    """F.interpolate(x, size=size, mode='bilinear') with the default align_corners=False."""
+    x = np.asarray(x, np.float64)
+    y0, y1, ly = _bilinear_taps(size[0], x.shape[-2])
+    x0, x1, lx = _bilinear_taps(size[1], x.shape[-1])
+    top = x[..., y0, :][..., :, x0] * (1 - lx) + x[..., y0, :][..., :, x1] * lx
+    bot = x[..., y1, :][..., :, x0] * (1 - lx) + x[..., y1, :][..., :, x1] * lx
+    return top * (1 - ly)[:, None] + bot * ly[:, None]
+
+
 def ffm_pattern(pool_vis, pool_ir, conv1_w, conv2_w):
     """models/common.py:434-516 (GPT1_fourier.forward between avgpool and the transformer), literally:
     pooled maps (B, C, h, w), conv1_w (8, C), conv2_w (C, 8) -> (token_embeddings (B, 2hw, C), pattenLoss).

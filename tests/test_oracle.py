@@ -120,6 +120,21 @@ def test_ffm_pattern_matches_reference(golden, tag):
     assert abs(loss - float(g["loss"][0])) <= 1e-5 * abs(float(g["loss"][0]))
 
 
+@pytest.mark.parametrize("shape,anchors", [((2, 3, 12, 10), (8, 8)), ((1, 2, 37, 53), (8, 8)), ((1, 1, 160, 160), (8, 8)),
+                                           ((2, 2, 8, 8), (8, 8)), ((1, 3, 9, 11), (1, 1)), ((1, 1, 33, 20), (4, 6))])
+def test_resample_oracle_matches_torch(shape, anchors):
+    """the pooling windows and bilinear taps the kernels implement == the torch ops the reference calls
+    (nn.AdaptiveAvgPool2d, common.py:324-325; F.interpolate bilinear, common.py:540-543)."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal(shape)
+    s = rng.standard_normal(shape[:2] + anchors)
+    assert relerr(O.adaptive_avg_pool2d(x, anchors), F.adaptive_avg_pool2d(torch.from_numpy(x), anchors).numpy()) <= 1e-12
+    want = F.interpolate(torch.from_numpy(s), size=list(shape[2:]), mode="bilinear").numpy()
+    assert relerr(O.upsample_bilinear(s, shape[2:]), want) <= 1e-12
+
+
 def test_causal_conv_oracle_matches_torch_conv1d():
     """the oracle's conv restatement vs the exact torch ops of models/mamba.py:176-180 (Conv1d padding=K-1, [:L], silu)."""
     import torch

@@ -300,3 +300,30 @@ def test_fourier_forward_graph_replay(golden):
         got = fast([vis, ir])
         for a, b in zip(got, want):
             assert torch.allclose(a, b, rtol=0, atol=0), seed
+
+
+def test_resample_fuzz_vs_oracle():
+    """random map / anchor-grid sizes (vector and scalar paths, more row groups than rows, single cells) for the four
+    directions: forward results vs the numpy oracle, backward results vs the adjoint identity <A x, g> = <x, A^T g>."""
+    from mmidet_b200 import ops
+    rng = np.random.default_rng(11)
+    for it in range(40):
+        hs, ws = int(rng.integers(1, 13)), int(rng.integers(1, 13))
+        H = int(rng.integers(hs, 70))
+        W = int(rng.integers(ws, 70)) if it % 3 else 4 * int(rng.integers((ws + 3) // 4, 18))
+        BC = (int(rng.integers(1, 4)), int(rng.integers(1, 6)))
+        x = rng.standard_normal(BC + (H, W)).astype(np.float32)
+        s = rng.standard_normal(BC + (hs, ws)).astype(np.float32)
+        xt, st = _t(x).requires_grad_(True), _t(s).requires_grad_(True)
+        pool, up = ops.adaptive_avg_pool(xt, (hs, ws)), ops.upsample_bilinear(st, (H, W))
+        tag = f"case {it}: {BC} {H}x{W} -> {hs}x{ws}"
+        assert relerr(pool.detach().cpu().numpy(), O.adaptive_avg_pool2d(x, (hs, ws))) <= 1e-5, tag
+        assert relerr(up.detach().cpu().numpy(), O.upsample_bilinear(s, (H, W))) <= 1e-5, tag
+        (dx,) = torch.autograd.grad(pool, xt, st.detach())   # A^T s
+        (ds,) = torch.autograd.grad(up, st, xt.detach())     # U^T x
+        lhs_p, rhs_p = float((pool.detach().double() * st.detach().double()).sum()), float((xt.detach().double() * dx.double()).sum())
+        lhs_u, rhs_u = float((up.detach().double() * xt.detach().double()).sum()), float((st.detach().double() * ds.double()).sum())
+        scale_p = float(pool.detach().abs().double().sum()) + 1.0
+        scale_u = float(up.detach().abs().double().sum()) + 1.0
+        assert abs(lhs_p - rhs_p) <= 1e-4 * scale_p, tag
+        assert abs(lhs_u - rhs_u) <= 1e-4 * scale_u, tag
