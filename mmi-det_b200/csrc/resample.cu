@@ -286,6 +286,109 @@ __global__ void __launch_bounds__(kRsThreads, 3)
     }
 }
 
+// Same map when two whole images fit in shared memory (160 x 160 fp32 does): the CTA streams its images through a
+// two-slot ring filled by 1-D bulk copies (cp.async.bulk, one mbarrier per slot), so the next image is in flight while
+// the current one is reduced out of shared memory -- the per-image tail no longer idles the memory system.  Vertical
+// taps first (thread = anchor row x four columns, 16-byte shared loads), then the horizontal taps as above.
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+constexpr int kRingThreads = 512;  // measured: 256 threads 0.060 ms (bilinear), 512 0.053 ms, 1024 with split supports 0.072 ms
+
+template <typename T>
+__global__ void __launch_bounds__(kRingThreads, 1)
+    resample_reduce_ring_kernel(const T *__restrict__ big, T *__restrict__ small, int BC, int H, int W, int hs, int ws,
+                                int mode, int R) {
+    extern __shared__ __align__(128) float sm[];
+    float *p = sm;
+    TapTable tx, ty;
+    tx.carve(p, W);
+    ty.carve(p, H);
+    int *xlo = reinterpret_cast<int *>(p), *xhi = xlo + ws, *ylo = xhi + ws, *yhi = ylo + hs;
+    p += 2 * ws + 2 * hs;
+    p = sm + (((p - sm) + 3) & ~3);
+    float *V = p;  // [R][hs][W]: vertical sums, the anchor row's support split into R parts
+    p += R * hs * W;
+    uint64_t *full = reinterpret_cast<uint64_t *>(p);
+    p += 4;
+    p = sm + (((p - sm) + 31) & ~31);  // 128-byte aligned slots
+    const uint32_t img_bytes = uint32_t(H) * W * sizeof(T);
+    unsigned char *slot0 = reinterpret_cast<unsigned char *>(p);
+    const uint32_t slot_stride = (img_bytes + 127u) & ~127u;
+    const int tid = threadIdx.x, W4 = W >> 2;
+
+    for (int i = tid; i < W; i += kRingThreads) taps(mode, i, W, ws, tx.t[i].i0, tx.t[i].i1, tx.t[i].w0, tx.t[i].w1);
+    for (int i = tid; i < H; i += kRingThreads) taps(mode, i, H, hs, ty.t[i].i0, ty.t[i].i1, ty.t[i].w0, ty.t[i].w1);
+    for (int j = tid; j < ws; j += kRingThreads) xlo[j] = 0, xhi[j] = -1;
+    for (int a = tid; a < hs; a += kRingThreads) ylo[a] = 0, yhi[a] = -1;
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    auto ends = [](const TapTable &t, int n, int *lo, int *hi, int i) {  // contiguous supports: one writer per end
+        const Tap e = t.at(i);
+        const int bins[2] = {e.i0, e.i1};
+        for (int k = 0; k < 2; ++k) {
+            const int bn = bins[k];
+            if (i == 0 || (t.at(i - 1).i0 != bn && t.at(i - 1).i1 != bn)) lo[bn] = i;
+            if (i == n - 1 || (t.at(i + 1).i0 != bn && t.at(i + 1).i1 != bn)) hi[bn] = i;
+        }
+    };
+    for (int x = tid; x < W; x += kRingThreads) ends(tx, W, xlo, xhi, x);
+    for (int y = tid; y < H; y += kRingThreads) ends(ty, H, ylo, yhi, y);
+    if (tid == 0 && int(blockIdx.x) < BC) {
+        mbar_arrive_expect_tx(&full[0], img_bytes);
+        bulk_load_1d(slot0, big + int64_t(blockIdx.x) * H * W, img_bytes, &full[0]);
+    }
+    __syncthreads();
+    const int parts = kRingThreads / (hs * ws) >= 32 ? 32 : (kRingThreads / (hs * ws) >= 16 ? 16 : (kRingThreads / (hs * ws) >= 8 ? 8 : 4));
+    int k = 0;
+    for (int im = blockIdx.x; im < BC; im += gridDim.x, ++k) {
+        const int nxt = im + gridDim.x;
+        if (tid == 0 && nxt < BC) {  // slot (k+1)&1 was drained before the barrier that ended iteration k-1
+            mbar_arrive_expect_tx(&full[(k + 1) & 1], img_bytes);
+            bulk_load_1d(slot0 + size_t((k + 1) & 1) * slot_stride, big + int64_t(nxt) * H * W, img_bytes, &full[(k + 1) & 1]);
+        }
+        mbar_wait(&full[k & 1], (k >> 1) & 1);
+        const T *img = reinterpret_cast<const T *>(slot0 + size_t(k & 1) * slot_stride);
+        for (int task = tid; task < R * hs * W4; task += kRingThreads) {
+            const int r = task / (hs * W4), a = (task / W4) % hs, q = task % W4;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int lo = ylo[a], n = yhi[a] - lo + 1;
+            const int ya = lo + (n * r) / R, yb = lo + (n * (r + 1)) / R;
+            for (int y = ya; y < yb; ++y) {
+                const float w = ty.weight(y, a);
+                const float4 v = load4<T>(img + y * W + 4 * q);
+                acc.x = fmaf(w, v.x, acc.x), acc.y = fmaf(w, v.y, acc.y), acc.z = fmaf(w, v.z, acc.z), acc.w = fmaf(w, v.w, acc.w);
+            }
+            *reinterpret_cast<float4 *>(V + (r * hs + a) * W + 4 * q) = acc;
+        }
+        __syncthreads();
+        T *dst = small + int64_t(im) * hs * ws;
+        for (int c0 = 0; c0 < hs * ws; c0 += kRingThreads / parts) {
+            const int cell = c0 + tid / parts, part = tid % parts;
+            float sacc = 0.f;
+            int a = 0, j = 0;
+            if (cell < hs * ws) {
+                a = cell / ws, j = cell % ws;
+                for (int x = xlo[j] + part; x <= xhi[j]; x += parts) {
+                    float v = V[a * W + x];
+                    for (int r = 1; r < R; ++r) v += V[(r * hs + a) * W + x];
+                    sacc = fmaf(tx.weight(x, j), v, sacc);
+                }
+            }
+            for (int o = 1; o < parts; o <<= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+            if (cell < hs * ws && part == 0) dst[a * ws + j] = from_f32<T>(sacc);
+        }
+        __syncthreads();  // V and slot k&1 are free again
+    }
+}
+
 // big[y, x] = sum Wy[i, y] Wx[j, x] small[i, j]; one CTA per image: horizontal pass into shared memory, then rows.
 template <typename T>
 __global__ void __launch_bounds__(kRsThreads)
@@ -397,9 +500,26 @@ int resample_reduce_launch(const void *big, void *small, int BC, int H, int W, i
     const bool rows = (W & 3) == 0 && RG >= 1 && smem_rows <= 160 * 1024;
     const size_t smem = rows ? smem_rows
                              : (size_t(4) * (H + W) + 2 * ws + hs * ws + kRsRows * ws + 4 + size_t(kRsRows) * (((W + 3) & ~3) + 4)) * sizeof(float);
+    // ring variant: two whole images + tables in shared memory, one CTA per SM walking over its images
+    const size_t esz = dtype == MMI_F32 ? 4 : 2;
+    const size_t img_b = (size_t(H) * W * esz + 127) & ~size_t(127);
+    int R = W4 > 0 ? kRingThreads / (hs * W4) : 1;
+    R = R < 1 ? 1 : (R > 4 ? 4 : R);
+    auto ring_bytes = [&](int r) {
+        return (size_t(4) * (H + W) + 2 * ws + 2 * hs + 4 + size_t(r) * hs * W + 4 + 32) * sizeof(float) + 2 * img_b;
+    };
+    while (R > 1 && ring_bytes(R) > 227 * 1024) --R;
+    const size_t smem_ring = ring_bytes(R);
+    const bool ring = (W & 3) == 0 && (size_t(H) * W * esz) % 16 == 0 && smem_ring <= 227 * 1024 && img_b >= 32 * 1024 &&
+                      BC >= 2 * sm_count();
 #define MMI_RS_REDUCE(T)                                                                                                \
     do {                                                                                                                \
-        if (rows) {                                                                                                     \
+        if (ring) {                                                                                                     \
+            auto kern = resample_reduce_ring_kernel<T>;                                                                 \
+            if (int e = opt_in_smem(kern, smem_ring)) return e;                                                         \
+            kern<<<min(BC, sm_count()), kRingThreads, smem_ring, st>>>(static_cast<const T *>(big), static_cast<T *>(small), BC, \
+                                                                        H, W, hs, ws, mode, R);                         \
+        } else if (rows) {                                                                                              \
             auto kern = resample_reduce_rows_kernel<T>;                                                                 \
             if (int e = opt_in_smem(kern, smem)) return e;                                                              \
             kern<<<min(BC, 3 * sm_count()), kRsThreads, smem, st>>>(static_cast<const T *>(big), static_cast<T *>(small), BC, H, W, hs, ws, mode, RG); \

@@ -220,7 +220,9 @@ def test_pattern_tokens_rejects_bad_input():
 # resampling either side of the FFM token path (models/common.py:324-325, :396-397, :540-543)
 # ---------------------------------------------------------------------------------------------------------
 _RESAMPLE_SHAPES = [((2, 3, 160, 160), (8, 8)), ((1, 5, 37, 53), (8, 8)), ((2, 4, 20, 24), (4, 6)), ((1, 2, 8, 8), (8, 8)),
-                    ((1, 3, 12, 10), (8, 8)), ((1, 1, 333, 64), (16, 16)), ((3, 2, 9, 11), (1, 1))]
+                    ((1, 3, 12, 10), (8, 8)), ((1, 1, 333, 64), (16, 16)), ((3, 2, 9, 11), (1, 1)),
+                    # >= 2 images per SM and >= 32 KB per image: the shared-memory ring variant of the reduce kernel
+                    ((4, 80, 96, 96), (8, 8)), ((2, 150, 128, 136), (8, 8)), ((5, 67, 100, 92), (5, 7))]
 
 
 @pytest.mark.parametrize("shape,anchors", _RESAMPLE_SHAPES)
