@@ -45,3 +45,45 @@ print(f"causal conv1d+SiLU fwd (B={Bc},L={Lc},ED={ED}) {t:.3f} ms = {byt/t/1e6:.
 conv = torch.nn.Conv1d(ED, ED, 4, groups=ED, padding=3).cuda()
 t2 = timeit(lambda: torch.nn.functional.silu(conv(x.transpose(1, 2))[:, :, :Lc].transpose(1, 2)).contiguous(), 10)
 print(f"  same op via transpose + nn.Conv1d + transpose + silu (stock PyTorch): {t2:.3f} ms")
+
+# ---- the remaining "next"-row kernels at the training shape of the P3 fusion block (16 pairs, 80x80 maps, d_model 256):
+# algorithmic bytes / time vs the measured HBM peak.  Working sets are >= 200 MB (> L2), timed back to back.
+PEAK = 6538.0
+
+
+def report(name, ms, nbytes, extra=""):
+    print(f"{name}: {ms:.3f} ms = {nbytes / ms / 1e6:.0f} GB/s = {nbytes / ms / 1e6 / PEAK * 100:.0f} % of the HBM peak{extra}")
+
+
+for dt in (torch.float32, torch.bfloat16):
+    es = torch.empty(0, dtype=dt).element_size()
+    tag = "fp32" if dt == torch.float32 else "bf16"
+    Bt, C, Hm, Wm = 16, 256, 80, 80
+    Lt, EDt = 2 * Hm * Wm, 2 * C
+    # causal conv backward: read x, dy; write dx (+ dw, dbias)
+    xc = torch.randn(Bt, Lt, EDt, device=dev, dtype=dt, requires_grad=True)
+    wc = torch.randn(EDt, 1, 4, device=dev, requires_grad=True); bcv = torch.randn(EDt, device=dev, requires_grad=True)
+    yc = ops.causal_conv1d_silu(xc, wc, bcv)
+    gy = torch.randn_like(yc)
+    t = timeit(lambda: torch.autograd.grad(yc, (xc, wc, bcv), gy, retain_graph=True), 20)
+    report(f"causal conv1d+SiLU bwd {tag} (B={Bt},L={Lt},ED={EDt})", t, 3 * Bt * Lt * EDt * es)
+    t = timeit(lambda: ops.causal_conv1d_silu(xc, wc, bcv), 20)
+    report(f"causal conv1d+SiLU fwd {tag} (same shape)", t, 2 * Bt * Lt * EDt * es)
+    # RMSNorm on the token stream (B, L, d_model)
+    xr = torch.randn(Bt, Lt, C, device=dev, dtype=dt, requires_grad=True)
+    wr = torch.ones(C, device=dev, requires_grad=True)
+    yr = ops.rmsnorm(xr, wr)
+    gr = torch.randn_like(yr)
+    t = timeit(lambda: ops.rmsnorm(xr, wr), 20)
+    report(f"RMSNorm fwd {tag} (B={Bt},L={Lt},C={C})", t, 2 * Bt * Lt * C * es)
+    t = timeit(lambda: torch.autograd.grad(yr, (xr, wr), gr, retain_graph=True), 20)
+    report(f"RMSNorm bwd {tag}", t, 3 * Bt * Lt * C * es)
+    # token layout: two NCHW maps <-> (B, 2HW, C) tokens
+    rgb = torch.randn(Bt, C, Hm, Wm, device=dev, dtype=dt); ir = torch.randn_like(rgb)
+    tok = ops.tokens_gather(rgb, ir)
+    t = timeit(lambda: ops.tokens_gather(rgb, ir), 20)
+    report(f"tokens gather {tag} (2 x ({Bt},{C},{Hm},{Wm}) -> ({Bt},{Lt},{C}))", t, 2 * tok.numel() * es)
+    t2 = timeit(lambda: torch.cat([rgb.flatten(2), ir.flatten(2)], dim=2).transpose(1, 2).contiguous(), 20)
+    print(f"  same layout change in stock torch (flatten / cat / transpose / contiguous): {t2:.3f} ms")
+    t = timeit(lambda: ops.tokens_scatter(tok, rgb.shape), 20)
+    report(f"tokens scatter {tag}", t, 2 * tok.numel() * es)

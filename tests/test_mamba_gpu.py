@@ -150,7 +150,8 @@ def test_rmsnorm_vs_torch_fp64(rows, C, dtype, tol):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("shape", [(2, 16, 6, 5), (1, 72, 7, 9), (3, 256, 20, 20)])
+@pytest.mark.parametrize("shape", [(2, 16, 6, 5), (1, 72, 7, 9), (3, 256, 20, 20), (2, 136, 12, 14), (1, 8, 4, 4),
+                                   (2, 64, 80, 80), (1, 200, 16, 17)])  # 16-byte-vector path with partial tiles, and scalar path
 def test_tokens_gather_scatter(shape, dtype):
     """token layout kernels == flatten / cat / transpose of models/common.py:1338-1343 (bit-exact: pure data movement), the
     scatter inverts the gather, and each is the other's adjoint under autograd."""
