@@ -22,20 +22,22 @@ constexpr int kConvWarps = 4;   // time segments per block
 template <typename T> struct Vec4;
 template <> struct Vec4<float> {
     using type = float4;
-    static __device__ __forceinline__ void load(const float *p, float (&v)[4]) {
-        const float4 q = __ldg(reinterpret_cast<const float4 *>(p));
-        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-    }
+    using raw = float4;
+    static __device__ __forceinline__ raw ldraw(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+    static __device__ __forceinline__ void unpack(const raw &q, float (&v)[4]) { v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+    static __device__ __forceinline__ void load(const float *p, float (&v)[4]) { unpack(ldraw(p), v); }
     static __device__ __forceinline__ void store(float *p, const float (&v)[4]) {
         __stcs(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3]));
     }
 };
 template <> struct Vec4<__nv_bfloat16> {
-    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float (&v)[4]) {
-        const uint2 q = __ldg(reinterpret_cast<const uint2 *>(p));
+    using raw = uint2;
+    static __device__ __forceinline__ raw ldraw(const __nv_bfloat16 *p) { return __ldg(reinterpret_cast<const uint2 *>(p)); }
+    static __device__ __forceinline__ void unpack(const raw &q, float (&v)[4]) {
         v[0] = __uint_as_float(q.x << 16); v[1] = __uint_as_float(q.x & 0xffff0000u);
         v[2] = __uint_as_float(q.y << 16); v[3] = __uint_as_float(q.y & 0xffff0000u);
     }
+    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float (&v)[4]) { unpack(ldraw(p), v); }
     static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float (&v)[4]) {
         const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
         uint2 q;
@@ -45,11 +47,13 @@ template <> struct Vec4<__nv_bfloat16> {
     }
 };
 template <> struct Vec4<__half> {
-    static __device__ __forceinline__ void load(const __half *p, float (&v)[4]) {
-        const uint2 q = __ldg(reinterpret_cast<const uint2 *>(p));
+    using raw = uint2;
+    static __device__ __forceinline__ raw ldraw(const __half *p) { return __ldg(reinterpret_cast<const uint2 *>(p)); }
+    static __device__ __forceinline__ void unpack(const raw &q, float (&v)[4]) {
         const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&q.x)), b = __half22float2(*reinterpret_cast<const __half2 *>(&q.y));
         v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
     }
+    static __device__ __forceinline__ void load(const __half *p, float (&v)[4]) { unpack(ldraw(p), v); }
     static __device__ __forceinline__ void store(__half *p, const float (&v)[4]) {
         const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
         uint2 q;
@@ -147,8 +151,22 @@ template <typename T, int K> __global__ void __launch_bounds__(32 * kConvWarps) 
             const int t = t0 - (K - 1) + j;
             if (t >= 0) Vec4<T>::load(x + int64_t(t) * p.x_ld, xw[j + 1]);
         }
-        const int t1 = min(t0 + kConvSeg, p.L);
-        for (int t = t0; t < t1 + K - 1; ++t) {
+        const int t1 = min(t0 + kConvSeg, p.L), tend = t1 + K - 1;
+        // the walk is serial per thread: the x / dy rows of the next PB steps are requested (packed) before the first of
+        // them is used, otherwise every step waits out a full memory latency
+        constexpr int PB = sizeof(T) == 2 ? 8 : 4;
+        for (int tb = t0; tb < tend; tb += PB) {
+        typename Vec4<T>::raw xq[PB], gq[PB];
+#pragma unroll
+        for (int u = 0; u < PB; ++u)
+            if (tb + u < tend && tb + u < p.L) {
+                xq[u] = Vec4<T>::ldraw(x + int64_t(tb + u) * p.x_ld);
+                gq[u] = Vec4<T>::ldraw(dy + int64_t(tb + u) * p.dy_ld);
+            }
+#pragma unroll
+        for (int u = 0; u < PB; ++u) {
+            const int t = tb + u;
+            if (t >= tend) break;
 #pragma unroll
             for (int j = 0; j < K - 1; ++j)
 #pragma unroll
@@ -158,8 +176,8 @@ template <typename T, int K> __global__ void __launch_bounds__(32 * kConvWarps) 
                 }
             if (t < p.L) {
                 float g[4];
-                Vec4<T>::load(x + int64_t(t) * p.x_ld, xw[K - 1]);
-                Vec4<T>::load(dy + int64_t(t) * p.dy_ld, g);
+                Vec4<T>::unpack(xq[u], xw[K - 1]);
+                Vec4<T>::unpack(gq[u], g);
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
                     float pre = bs[v];
@@ -193,6 +211,7 @@ template <typename T, int K> __global__ void __launch_bounds__(32 * kConvWarps) 
                 }
                 Vec4<T>::store(dx + int64_t(s) * p.dx_ld, o);
             }
+        }
         }
     }
     // block reduction over the kConvWarps time segments, then one atomic per (channel, tap)

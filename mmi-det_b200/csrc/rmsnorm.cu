@@ -30,6 +30,24 @@ template <> __device__ __forceinline__ void rms_load4<__half>(const __half *p, f
     const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&q.x)), b = __half22float2(*reinterpret_cast<const __half2 *>(&q.y));
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
+// packed row fragments: requested several rows ahead and unpacked only when consumed (2 registers per 4 16-bit elements)
+template <typename T> struct RmsRaw { using type = uint2; };
+template <> struct RmsRaw<float> { using type = float4; };
+template <typename T> __device__ __forceinline__ typename RmsRaw<T>::type rms_ldraw(const T *p) {
+    return __ldg(reinterpret_cast<const typename RmsRaw<T>::type *>(p));
+}
+template <typename T> __device__ __forceinline__ void rms_unpack(const typename RmsRaw<T>::type &q, float (&v)[4]);
+template <> __device__ __forceinline__ void rms_unpack<float>(const float4 &q, float (&v)[4]) {
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+}
+template <> __device__ __forceinline__ void rms_unpack<__nv_bfloat16>(const uint2 &q, float (&v)[4]) {
+    v[0] = __uint_as_float(q.x << 16); v[1] = __uint_as_float(q.x & 0xffff0000u);
+    v[2] = __uint_as_float(q.y << 16); v[3] = __uint_as_float(q.y & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void rms_unpack<__half>(const uint2 &q, float (&v)[4]) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&q.x)), b = __half22float2(*reinterpret_cast<const __half2 *>(&q.y));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
 template <typename T> __device__ __forceinline__ void rms_store4(T *p, const float (&v)[4]);
 template <> __device__ __forceinline__ void rms_store4<float>(float *p, const float (&v)[4]) {
     *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
@@ -104,39 +122,59 @@ __global__ void __launch_bounds__(128) rmsnorm_bwd_kernel(const T *__restrict__ 
             wv[i][0] = ww.x; wv[i][1] = ww.y; wv[i][2] = ww.z; wv[i][3] = ww.w;
         }
     }
-    for (int rr = 0; rr < kRmsRowsPerWarp; ++rr) {
-        const int64_t row = row0 + rr;
-        if (row >= rows) break;
-        float xv[NV][4], gv[NV][4];
-        float ss = 0.f, sg = 0.f;
+    // Rows are independent but a warp walks its strip serially, and registers cap the resident warps (6 blocks per SM at
+    // NV = 2): bytes in flight = warps x rows in flight x row bytes.  Rows are therefore requested RB at a time, packed,
+    // before the first of them is reduced (one row at a time left 16-bit maps latency-bound at a third of the HBM peak).
+    using Raw = typename RmsRaw<T>::type;
+    constexpr int RB = NV <= 2 ? 4 : (NV == 4 ? 2 : 1);
+    const int nrow = int(min(int64_t(kRmsRowsPerWarp), rows - row0));
+    for (int r0 = 0; r0 < nrow; r0 += RB) {
+        Raw xq[RB][NV], gq[RB][NV];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int c = (i * 32 + lane) * 4;
-            if (c < C) {
-                rms_load4<T>(x + row * x_ld + c, xv[i]);
-                rms_load4<T>(dy + row * dy_ld + c, gv[i]);
+        for (int b = 0; b < RB; ++b)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    ss = fmaf(xv[i][k], xv[i][k], ss);
-                    sg = fmaf(gv[i][k] * wv[i][k], xv[i][k], sg);
+            for (int i = 0; i < NV; ++i) {
+                const int c = (i * 32 + lane) * 4;
+                if (r0 + b < nrow && c < C) {
+                    xq[b][i] = rms_ldraw<T>(x + (row0 + r0 + b) * x_ld + c);
+                    gq[b][i] = rms_ldraw<T>(dy + (row0 + r0 + b) * dy_ld + c);
                 }
             }
-        }
-        ss = warp_sum(ss);
-        sg = warp_sum(sg);
-        const float r = rsqrtf(ss / float(C) + eps);
-        const float coef = r * r * r * sg / float(C);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int c = (i * 32 + lane) * 4;
-            if (c < C) {
-                float o[4];
+        for (int b = 0; b < RB; ++b) {
+            if (r0 + b >= nrow) break;
+            const int64_t row = row0 + r0 + b;
+            float xv[NV][4], gv[NV][4];
+            float ss = 0.f, sg = 0.f;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    o[k] = fmaf(gv[i][k] * wv[i][k], r, -xv[i][k] * coef);
-                    dwa[i][k] = fmaf(gv[i][k] * r, xv[i][k], dwa[i][k]);
+            for (int i = 0; i < NV; ++i) {
+                const int c = (i * 32 + lane) * 4;
+                if (c < C) {
+                    rms_unpack<T>(xq[b][i], xv[i]);
+                    rms_unpack<T>(gq[b][i], gv[i]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        ss = fmaf(xv[i][k], xv[i][k], ss);
+                        sg = fmaf(gv[i][k] * wv[i][k], xv[i][k], sg);
+                    }
                 }
-                rms_store4<T>(dx + row * dx_ld + c, o);
+            }
+            ss = warp_sum(ss);
+            sg = warp_sum(sg);
+            const float r = rsqrtf(ss / float(C) + eps);
+            const float coef = r * r * r * sg / float(C);
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int c = (i * 32 + lane) * 4;
+                if (c < C) {
+                    float o[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        o[k] = fmaf(gv[i][k] * wv[i][k], r, -xv[i][k] * coef);
+                        dwa[i][k] = fmaf(gv[i][k] * r, xv[i][k], dwa[i][k]);
+                    }
+                    rms_store4<T>(dx + row * dx_ld + c, o);
+                }
             }
         }
     }

@@ -87,3 +87,25 @@ for dt in (torch.float32, torch.bfloat16):
     print(f"  same layout change in stock torch (flatten / cat / transpose / contiguous): {t2:.3f} ms")
     t = timeit(lambda: ops.tokens_scatter(tok, rgb.shape), 20)
     report(f"tokens scatter {tag}", t, 2 * tok.numel() * es)
+
+    # kernel-only times of the two backward kernels (direct C-ABI calls on preallocated buffers: the autograd path above
+    # adds 60-100 us of host work per call, which hides kernels this short)
+    from mmidet_b200 import _lib
+    lib = _lib.load()
+    P, DT, ST = ops._ptr, ops._DT, ops._stream
+    x2, g2 = xr.detach().reshape(-1, C), gr.reshape(-1, C)
+    dx2, dw2 = torch.empty_like(x2), torch.empty(C, device=dev)
+    w32 = wr.detach().float()
+    t = timeit(lambda: lib.mmi_rmsnorm_bwd(P(x2), P(w32), P(g2), P(dx2), P(dw2), x2.shape[0], C, x2.stride(0), g2.stride(0),
+                                           dx2.stride(0), 1e-5, DT[dt], ST(x2)), 20)
+    report(f"RMSNorm bwd kernel only {tag}", t, 3 * Bt * Lt * C * es)
+    xc2, gy2 = xc.detach(), gy
+    dxc, dwc, dbc = torch.empty_like(xc2), torch.empty(EDt, 4, device=dev), torch.empty(EDt, device=dev)
+    wc2, bc2 = wc.detach().reshape(EDt, 4).contiguous(), bcv.detach()
+    t = timeit(lambda: lib.mmi_causal_conv1d_bwd(P(xc2), P(wc2), P(bc2), P(gy2), P(dxc), P(dwc), P(dbc), Bt, Lt, EDt, 4, xc2.stride(1),
+                                                 gy2.stride(1), dxc.stride(1), DT[dt], 1, ST(xc2)), 20)
+    report(f"causal conv1d+SiLU bwd kernel only {tag}", t, 3 * Bt * Lt * EDt * es)
+    yc2 = torch.empty_like(xc2)
+    t = timeit(lambda: lib.mmi_causal_conv1d_fwd(P(xc2), P(wc2), P(bc2), P(yc2), Bt, Lt, EDt, 4, xc2.stride(1), yc2.stride(1), DT[dt], 1,
+                                                 ST(xc2)), 20)
+    report(f"causal conv1d+SiLU fwd kernel only {tag}", t, 2 * Bt * Lt * EDt * es)
