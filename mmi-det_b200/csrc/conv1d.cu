@@ -97,22 +97,31 @@ template <typename T, int K> __global__ void __launch_bounds__(32 * kConvWarps) 
             for (int v = 0; v < 4; ++v) win[j + 1][v] = 0.f;
     }
     const int t1 = min(t0 + kConvSeg, p.L);
-#pragma unroll 4
-    for (int t = t0; t < t1; ++t) {
+    constexpr int PB = sizeof(T) == 2 ? 8 : 4;  // rows requested ahead of their use (packed), see the backward kernel
+    for (int tb = t0; tb < t1; tb += PB) {
+        typename Vec4<T>::raw xq[PB];
 #pragma unroll
-        for (int j = 0; j < K - 1; ++j)
+        for (int u = 0; u < PB; ++u)
+            if (tb + u < t1) xq[u] = Vec4<T>::ldraw(x + int64_t(tb + u) * p.x_ld);
 #pragma unroll
-            for (int v = 0; v < 4; ++v) win[j][v] = win[j + 1][v];
-        Vec4<T>::load(x + int64_t(t) * p.x_ld, win[K - 1]);
-        float o[4];
+        for (int u = 0; u < PB; ++u) {
+            const int t = tb + u;
+            if (t >= t1) break;
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            float acc = bs[v];
+            for (int j = 0; j < K - 1; ++j)
 #pragma unroll
-            for (int j = 0; j < K; ++j) acc = fmaf(w[j][v], win[j][v], acc);
-            o[v] = p.silu ? acc * sigmoidf_fast(acc) : acc;
+                for (int v = 0; v < 4; ++v) win[j][v] = win[j + 1][v];
+            Vec4<T>::unpack(xq[u], win[K - 1]);
+            float o[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                float acc = bs[v];
+#pragma unroll
+                for (int j = 0; j < K; ++j) acc = fmaf(w[j][v], win[j][v], acc);
+                o[v] = p.silu ? acc * sigmoidf_fast(acc) : acc;
+            }
+            Vec4<T>::store(y + int64_t(t) * p.y_ld, o);
         }
-        Vec4<T>::store(y + int64_t(t) * p.y_ld, o);
     }
 }
 
