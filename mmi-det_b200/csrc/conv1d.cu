@@ -87,14 +87,16 @@ template <typename T, int K> __global__ void __launch_bounds__(32 * kConvWarps) 
     }
     const T *x = static_cast<const T *>(p.x) + int64_t(b) * p.L * p.x_ld + c;
     T *y = static_cast<T *>(p.y) + int64_t(b) * p.L * p.y_ld + c;
-    float win[K][4];  // win[j] = x[t - (K-1) + j]
+    // x of the last four steps lives in a ring indexed by (t - t0) & 3; the step loop is unrolled in multiples of four,
+    // so every ring index is a compile-time constant and nothing is shifted between steps
+    float ring[4][4];
 #pragma unroll
-    for (int j = 0; j < K - 1; ++j) {
-        const int t = t0 - (K - 1) + j;
-        if (t >= 0) Vec4<T>::load(x + int64_t(t) * p.x_ld, win[j + 1]);
+    for (int m = 1; m < K; ++m) {
+        const int t = t0 - m;
+        if (t >= 0) Vec4<T>::load(x + int64_t(t) * p.x_ld, ring[(4 - m) & 3]);
         else
 #pragma unroll
-            for (int v = 0; v < 4; ++v) win[j + 1][v] = 0.f;
+            for (int v = 0; v < 4; ++v) ring[(4 - m) & 3][v] = 0.f;
     }
     const int t1 = min(t0 + kConvSeg, p.L);
     constexpr int PB = sizeof(T) == 2 ? 8 : 4;  // rows requested ahead of their use (packed), see the backward kernel
@@ -106,21 +108,18 @@ template <typename T, int K> __global__ void __launch_bounds__(32 * kConvWarps) 
 #pragma unroll
         for (int u = 0; u < PB; ++u) {
             const int t = tb + u;
-            if (t >= t1) break;
+            if (t < t1) {
+                Vec4<T>::unpack(xq[u], ring[u & 3]);
+                float o[4];
 #pragma unroll
-            for (int j = 0; j < K - 1; ++j)
+                for (int v = 0; v < 4; ++v) {
+                    float acc = bs[v];
 #pragma unroll
-                for (int v = 0; v < 4; ++v) win[j][v] = win[j + 1][v];
-            Vec4<T>::unpack(xq[u], win[K - 1]);
-            float o[4];
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                float acc = bs[v];
-#pragma unroll
-                for (int j = 0; j < K; ++j) acc = fmaf(w[j][v], win[j][v], acc);
-                o[v] = p.silu ? acc * sigmoidf_fast(acc) : acc;
+                    for (int j = 0; j < K; ++j) acc = fmaf(w[j][v], ring[(u - (K - 1) + j) & 3][v], acc);  // x[t-(K-1)+j]
+                    o[v] = p.silu ? acc * sigmoidf_fast(acc) : acc;
+                }
+                Vec4<T>::store(y + int64_t(t) * p.y_ld, o);
             }
-            Vec4<T>::store(y + int64_t(t) * p.y_ld, o);
         }
     }
 }
@@ -150,77 +149,73 @@ template <typename T, int K> __global__ void __launch_bounds__(32 * kConvWarps) 
         const T *dy = static_cast<const T *>(p.dy) + int64_t(b) * p.L * p.dy_ld + c;
         T *dx = static_cast<T *>(p.dx) + int64_t(b) * p.L * p.dx_ld + c;
         // walk t = t0 .. t1 + K - 2: dpre[t] needs x[t-K+1 .. t]; dx[s] (s = t - K + 1) needs dpre[s .. s+K-1]
-        float xw[K][4], dp[K][4];  // xw[j] = x[t-(K-1)+j]; dp[j] = dpre[t-(K-1)+j]
+        // x and dpre of the last four steps live in rings indexed by (t - t0) & 3 (compile-time constants after unrolling
+        // in multiples of four: no register shifting between steps)
+        float xr[4][4], dr[4][4];
 #pragma unroll
-        for (int j = 0; j < K; ++j)
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int v = 0; v < 4; ++v) xw[j][v] = dp[j][v] = 0.f;
+            for (int v = 0; v < 4; ++v) xr[j][v] = dr[j][v] = 0.f;
 #pragma unroll
-        for (int j = 0; j < K - 1; ++j) {
-            const int t = t0 - (K - 1) + j;
-            if (t >= 0) Vec4<T>::load(x + int64_t(t) * p.x_ld, xw[j + 1]);
+        for (int m = 1; m < K; ++m) {
+            const int t = t0 - m;
+            if (t >= 0) Vec4<T>::load(x + int64_t(t) * p.x_ld, xr[(4 - m) & 3]);
         }
         const int t1 = min(t0 + kConvSeg, p.L), tend = t1 + K - 1;
         // the walk is serial per thread: the x / dy rows of the next PB steps are requested (packed) before the first of
         // them is used, otherwise every step waits out a full memory latency
         constexpr int PB = sizeof(T) == 2 ? 8 : 4;
         for (int tb = t0; tb < tend; tb += PB) {
-        typename Vec4<T>::raw xq[PB], gq[PB];
+            typename Vec4<T>::raw xq[PB], gq[PB];
 #pragma unroll
-        for (int u = 0; u < PB; ++u)
-            if (tb + u < tend && tb + u < p.L) {
-                xq[u] = Vec4<T>::ldraw(x + int64_t(tb + u) * p.x_ld);
-                gq[u] = Vec4<T>::ldraw(dy + int64_t(tb + u) * p.dy_ld);
-            }
-#pragma unroll
-        for (int u = 0; u < PB; ++u) {
-            const int t = tb + u;
-            if (t >= tend) break;
-#pragma unroll
-            for (int j = 0; j < K - 1; ++j)
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    xw[j][v] = xw[j + 1][v];
-                    dp[j][v] = dp[j + 1][v];
+            for (int u = 0; u < PB; ++u)
+                if (tb + u < tend && tb + u < p.L) {
+                    xq[u] = Vec4<T>::ldraw(x + int64_t(tb + u) * p.x_ld);
+                    gq[u] = Vec4<T>::ldraw(dy + int64_t(tb + u) * p.dy_ld);
                 }
-            if (t < p.L) {
-                float g[4];
-                Vec4<T>::unpack(xq[u], xw[K - 1]);
-                Vec4<T>::unpack(gq[u], g);
 #pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    float pre = bs[v];
+            for (int u = 0; u < PB; ++u) {
+                const int t = tb + u;
+                if (t < tend) {
+                    if (t < p.L) {
+                        float g[4];
+                        Vec4<T>::unpack(xq[u], xr[u & 3]);
+                        Vec4<T>::unpack(gq[u], g);
 #pragma unroll
-                    for (int j = 0; j < K; ++j) pre = fmaf(w[j][v], xw[j][v], pre);
-                    float d = g[v];
-                    if (p.silu) {
-                        const float s = sigmoidf_fast(pre);
-                        d *= s * fmaf(pre, 1.f - s, 1.f);
+                        for (int v = 0; v < 4; ++v) {
+                            float pre = bs[v];
+#pragma unroll
+                            for (int j = 0; j < K; ++j) pre = fmaf(w[j][v], xr[(u - (K - 1) + j) & 3][v], pre);
+                            float d = g[v];
+                            if (p.silu) {
+                                const float sg = sigmoidf_fast(pre);
+                                d *= sg * fmaf(pre, 1.f - sg, 1.f);
+                            }
+                            dr[u & 3][v] = d;
+                            if (t < t1) {  // parameter gradients: own segment only (halo steps belong to the next segment)
+                                dba[v] += d;
+#pragma unroll
+                                for (int j = 0; j < K; ++j) dwa[j][v] = fmaf(d, xr[(u - (K - 1) + j) & 3][v], dwa[j][v]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) xr[u & 3][v] = dr[u & 3][v] = 0.f;
                     }
-                    dp[K - 1][v] = d;
-                    if (t < t1) {  // parameter gradients: own segment only (halo steps belong to the next segment)
-                        dba[v] += d;
+                    const int sx = t - (K - 1);
+                    if (sx >= t0) {  // dx[s] = sum_j w[j] * dpre[s + K-1 - j] = sum_j w[j] * dpre[t - j]
+                        float o[4];
 #pragma unroll
-                        for (int j = 0; j < K; ++j) dwa[j][v] = fmaf(d, xw[j][v], dwa[j][v]);
+                        for (int v = 0; v < 4; ++v) {
+                            float acc = 0.f;
+#pragma unroll
+                            for (int j = 0; j < K; ++j) acc = fmaf(w[j][v], dr[(u - j) & 3][v], acc);
+                            o[v] = acc;
+                        }
+                        Vec4<T>::store(dx + int64_t(sx) * p.dx_ld, o);
                     }
                 }
-            } else {
-#pragma unroll
-                for (int v = 0; v < 4; ++v) xw[K - 1][v] = dp[K - 1][v] = 0.f;
             }
-            const int s = t - (K - 1);
-            if (s >= t0) {  // dx[s] = sum_j w[j] * dpre[s + K-1 - j] = sum_j w[j] * dp[K-1-j]
-                float o[4];
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    float acc = 0.f;
-#pragma unroll
-                    for (int j = 0; j < K; ++j) acc = fmaf(w[j][v], dp[K - 1 - j][v], acc);
-                    o[v] = acc;
-                }
-                Vec4<T>::store(dx + int64_t(s) * p.dx_ld, o);
-            }
-        }
         }
     }
     // block reduction over the kConvWarps time segments, then one atomic per (channel, tap)
