@@ -105,8 +105,15 @@ class MambaBlock(nn.Module):
         A = -torch.exp(self.A_log.float())
         dbc = self.x_proj(x)
         delta, B, C = torch.split(dbc, [c.dt_rank, c.d_state, c.d_state], dim=-1)
-        # softplus(dt_proj(.)) of models/mamba.py:203 is applied inside the scan kernels (no elementwise pass, no cast)
-        return self.selective_scan(x, self.dt_proj(delta), A, B, C, self.D.float(), z=z, delta_softplus=True)
+        # dt_proj on the low-rank slice as ONE addmm (bias in the GEMM epilogue): F.linear on this strided view otherwise
+        # runs matmul + a separate broadcast bias pass over (B, L, ED).  softplus(dt_proj(.)) of models/mamba.py:203 is
+        # applied inside the scan kernels (no elementwise pass, no cast).
+        dtp = self.dt_proj
+        if dtp.bias is not None and delta.dim() == 3:
+            delta_pre = torch.addmm(dtp.bias, delta.reshape(-1, c.dt_rank), dtp.weight.t()).view(*delta.shape[:-1], -1)
+        else:
+            delta_pre = dtp(delta)
+        return self.selective_scan(x, delta_pre, A, B, C, self.D.float(), z=z, delta_softplus=True)
 
     def forward(self, x):
         L = x.shape[1]
