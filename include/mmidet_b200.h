@@ -172,11 +172,14 @@ int mmi_causal_conv1d_bwd(const void *x, const float *w, const float *bias, cons
  * RMSNorm over the last axis of (rows, C) tokens.  Replaces RMSNorm.forward (models/mamba.py:356-366):
  *     y = x * rsqrt(mean(x^2, -1) + eps) * w          x, y, dy, dx : (rows, C) dtype with row pitches in elements; w (C) fp32
  * The backward overwrites dx and dw (C) fp32 (summed with fp32 atomics).  C a multiple of 8, C <= 1024.
+ * y_dtype / dy_dtype: element type of y (forward) and dy (backward); -1 or `dtype` for the same type as x, or a 16-bit
+ * type with fp32 x -- the autocast case, where the fp32 norm feeds a 16-bit GEMM: the kernel rounds once in its store
+ * (identical to an fp32 result followed by a cast) and reads the 16-bit gradient directly, saving a pass each way.
  * --------------------------------------------------------------------------------------------------------- */
 int mmi_rmsnorm_fwd(const void *x, const float *w, void *y, int64_t rows, int C, int64_t x_ld, int64_t y_ld, float eps, int dtype,
-                    void *stream);
+                    int y_dtype, void *stream);
 int mmi_rmsnorm_bwd(const void *x, const float *w, const void *dy, void *dx, float *dw, int64_t rows, int C, int64_t x_ld,
-                    int64_t dy_ld, int64_t dx_ld, float eps, int dtype, void *stream);
+                    int64_t dy_ld, int64_t dx_ld, float eps, int dtype, int dy_dtype, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Token layout either side of the fusion block.  Replaces flatten / cat / permute / contiguous of

@@ -100,8 +100,8 @@ _SIGNATURES = {
     "mmi_ffm_pattern_bwd": (_i, [_vp] * 11 + [_i] * 4 + [_vp]),
     "mmi_causal_conv1d_fwd": (_i, [_vp] * 4 + [_i] * 4 + [_i64] * 2 + [_i] * 2 + [_vp]),
     "mmi_causal_conv1d_bwd": (_i, [_vp] * 7 + [_i] * 4 + [_i64] * 3 + [_i] * 2 + [_vp]),
-    "mmi_rmsnorm_fwd": (_i, [_vp] * 3 + [_i64, _i, _i64, _i64, _c.c_float, _i, _vp]),
-    "mmi_rmsnorm_bwd": (_i, [_vp] * 5 + [_i64, _i, _i64, _i64, _i64, _c.c_float, _i, _vp]),
+    "mmi_rmsnorm_fwd": (_i, [_vp] * 3 + [_i64, _i, _i64, _i64, _c.c_float, _i, _i, _vp]),
+    "mmi_rmsnorm_bwd": (_i, [_vp] * 5 + [_i64, _i, _i64, _i64, _i64, _c.c_float, _i, _i, _vp]),
     "mmi_tokens_gather": (_i, [_vp] * 3 + [_i] * 4 + [_vp]),
     "mmi_tokens_scatter": (_i, [_vp] * 3 + [_i] * 4 + [_vp]),
     "mmi_selscan_fwd_bwd_host": (_i, [_vp] * 16 + [_i] * 6),

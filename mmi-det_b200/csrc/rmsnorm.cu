@@ -74,8 +74,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // NV = number of float4 groups per lane actually used (C <= 128 * NV); rows = B * L, x/y row pitches in elements
-template <typename T, int NV>
-__global__ void __launch_bounds__(128) rmsnorm_fwd_kernel(const T *__restrict__ x, const float *__restrict__ w, T *__restrict__ y,
+template <typename T, typename TY, int NV>
+__global__ void __launch_bounds__(128) rmsnorm_fwd_kernel(const T *__restrict__ x, const float *__restrict__ w, TY *__restrict__ y,
                                                           float *__restrict__ rstd, int64_t rows, int C, int64_t x_ld, int64_t y_ld,
                                                           float eps) {
     const int lane = threadIdx.x & 31;
@@ -100,13 +100,13 @@ __global__ void __launch_bounds__(128) rmsnorm_fwd_kernel(const T *__restrict__ 
         if (c < C) {
             const float4 ww = __ldg(reinterpret_cast<const float4 *>(w + c));
             float o[4] = {v[i][0] * r * ww.x, v[i][1] * r * ww.y, v[i][2] * r * ww.z, v[i][3] * r * ww.w};
-            rms_store4<T>(y + row * y_ld + c, o);
+            rms_store4<TY>(y + row * y_ld + c, o);
         }
     }
 }
 
-template <typename T, int NV>
-__global__ void __launch_bounds__(128) rmsnorm_bwd_kernel(const T *__restrict__ x, const float *__restrict__ w, const T *__restrict__ dy,
+template <typename T, typename TY, int NV>
+__global__ void __launch_bounds__(128) rmsnorm_bwd_kernel(const T *__restrict__ x, const float *__restrict__ w, const TY *__restrict__ dy,
                                                           T *__restrict__ dx, float *__restrict__ dw, int64_t rows, int C, int64_t x_ld,
                                                           int64_t dy_ld, int64_t dx_ld, float eps) {
     const int lane = threadIdx.x & 31;
@@ -126,10 +126,12 @@ __global__ void __launch_bounds__(128) rmsnorm_bwd_kernel(const T *__restrict__ 
     // NV = 2): bytes in flight = warps x rows in flight x row bytes.  Rows are therefore requested RB at a time, packed,
     // before the first of them is reduced (one row at a time left 16-bit maps latency-bound at a third of the HBM peak).
     using Raw = typename RmsRaw<T>::type;
+    using RawY = typename RmsRaw<TY>::type;
     constexpr int RB = NV <= 2 ? 4 : (NV == 4 ? 2 : 1);
     const int nrow = int(min(int64_t(kRmsRowsPerWarp), rows - row0));
     for (int r0 = 0; r0 < nrow; r0 += RB) {
-        Raw xq[RB][NV], gq[RB][NV];
+        Raw xq[RB][NV];
+        RawY gq[RB][NV];
 #pragma unroll
         for (int b = 0; b < RB; ++b)
 #pragma unroll
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(128) rmsnorm_bwd_kernel(const T *__restrict__ 
                 const int c = (i * 32 + lane) * 4;
                 if (r0 + b < nrow && c < C) {
                     xq[b][i] = rms_ldraw<T>(x + (row0 + r0 + b) * x_ld + c);
-                    gq[b][i] = rms_ldraw<T>(dy + (row0 + r0 + b) * dy_ld + c);
+                    gq[b][i] = rms_ldraw<TY>(dy + (row0 + r0 + b) * dy_ld + c);
                 }
             }
 #pragma unroll
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(128) rmsnorm_bwd_kernel(const T *__restrict__ 
                 const int c = (i * 32 + lane) * 4;
                 if (c < C) {
                     rms_unpack<T>(xq[b][i], xv[i]);
-                    rms_unpack<T>(gq[b][i], gv[i]);
+                    rms_unpack<TY>(gq[b][i], gv[i]);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         ss = fmaf(xv[i][k], xv[i][k], ss);
@@ -199,18 +201,22 @@ __global__ void __launch_bounds__(128) rmsnorm_bwd_kernel(const T *__restrict__ 
     }
 }
 
-template <typename T> static int rms_launch_t(bool bwd, const void *x, const float *w, const void *dy, void *out, float *dw, int64_t rows,
-                                              int C, int64_t x_ld, int64_t dy_ld, int64_t out_ld, float eps, cudaStream_t st) {
+// T: dtype of x / dx; TY: dtype of y (forward) and dy (backward) -- equal to T, or 16-bit with fp32 x (autocast: the
+// norm runs in fp32 and its output is consumed by a 16-bit GEMM, so the rounding happens in the kernel's store)
+template <typename T, typename TY> static int rms_launch_t(bool bwd, const void *x, const float *w, const void *dy, void *out, float *dw,
+                                                           int64_t rows, int C, int64_t x_ld, int64_t dy_ld, int64_t out_ld, float eps,
+                                                           cudaStream_t st) {
     const T *xp = static_cast<const T *>(x);
-    const T *gp = static_cast<const T *>(dy);
-    T *op = static_cast<T *>(out);
     if (bwd)
         if (int e = check_cuda(cudaMemsetAsync(dw, 0, size_t(C) * 4, st), "rmsnorm dw memset")) return e;
     const unsigned gf = unsigned((rows + 3) / 4), gb = unsigned((rows + 4 * kRmsRowsPerWarp - 1) / (4 * kRmsRowsPerWarp));
 #define MMI_RMS(NVV)                                                                                                   \
     if (C <= 128 * NVV) {                                                                                              \
-        if (bwd) rmsnorm_bwd_kernel<T, NVV><<<gb, 128, 0, st>>>(xp, w, gp, op, dw, rows, C, x_ld, dy_ld, out_ld, eps); \
-        else rmsnorm_fwd_kernel<T, NVV><<<gf, 128, 0, st>>>(xp, w, op, nullptr, rows, C, x_ld, out_ld, eps);           \
+        if (bwd)                                                                                                       \
+            rmsnorm_bwd_kernel<T, TY, NVV><<<gb, 128, 0, st>>>(xp, w, static_cast<const TY *>(dy), static_cast<T *>(out), dw, rows, C, \
+                                                               x_ld, dy_ld, out_ld, eps);                              \
+        else                                                                                                           \
+            rmsnorm_fwd_kernel<T, TY, NVV><<<gf, 128, 0, st>>>(xp, w, static_cast<TY *>(out), nullptr, rows, C, x_ld, out_ld, eps); \
         return check_cuda(cudaGetLastError(), "rmsnorm launch");                                                      \
     }
     MMI_RMS(1)
@@ -222,17 +228,35 @@ template <typename T> static int rms_launch_t(bool bwd, const void *x, const flo
     return MMI_ERR_UNSUPPORTED;
 }
 
+static int rms_dispatch(bool bwd, const void *x, const float *w, const void *dy, void *out, float *dw, int64_t rows, int C,
+                        int64_t x_ld, int64_t dy_ld, int64_t out_ld, float eps, int dtype, int y_dtype, cudaStream_t st) {
+#define MMI_RMS_GO(T, TY) return rms_launch_t<T, TY>(bwd, x, w, dy, out, dw, rows, C, x_ld, dy_ld, out_ld, eps, st)
+    if (y_dtype == dtype) {
+        if (dtype == MMI_F32) MMI_RMS_GO(float, float);
+        if (dtype == MMI_BF16) MMI_RMS_GO(__nv_bfloat16, __nv_bfloat16);
+        MMI_RMS_GO(__half, __half);
+    }
+    if (dtype == MMI_F32 && y_dtype == MMI_BF16) MMI_RMS_GO(float, __nv_bfloat16);
+    if (dtype == MMI_F32 && y_dtype == MMI_F16) MMI_RMS_GO(float, __half);
+#undef MMI_RMS_GO
+    set_error("rmsnorm: unsupported dtype pair (x %d, y/dy %d): y/dy must match x, or be 16-bit with fp32 x", dtype, y_dtype);
+    return MMI_ERR_UNSUPPORTED;
+}
+
 }  // namespace mmi
 
 using namespace mmi;
 
 extern "C" {
 
-static int rms_check(const char *who, int64_t rows, int C, int dtype, const void *a, const void *b, int64_t lda, int64_t ldb) {
+static int rms_esize(int dtype) { return dtype == MMI_F32 ? 4 : (dtype == MMI_BF16 || dtype == MMI_F16) ? 2 : 0; }
+
+static int rms_check(const char *who, int64_t rows, int C, int dtype, int y_dtype, const void *a, const void *b, int64_t lda,
+                     int64_t ldb) {
     if (rows <= 0 || C <= 0 || C % 8) { set_error("%s: bad shape (rows=%lld C=%d; C must be a multiple of 8)", who, (long long)rows, C); return MMI_ERR_ARG; }
-    const int es = dtype == MMI_F32 ? 4 : (dtype == MMI_BF16 || dtype == MMI_F16) ? 2 : 0;
-    if (!es) { set_error("%s: unknown dtype %d", who, dtype); return MMI_ERR_ARG; }
-    if ((lda * es) % 16 || (ldb * es) % 16 || (reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) {
+    const int es = rms_esize(dtype), eb = rms_esize(y_dtype);
+    if (!es || !eb) { set_error("%s: unknown dtype %d / %d", who, dtype, y_dtype); return MMI_ERR_ARG; }
+    if ((lda * es) % 16 || (ldb * eb) % (eb == 2 ? 8 : 16) || (reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15)) {
         set_error("%s: rows must be 16-byte aligned", who);
         return MMI_ERR_ARG;
     }
@@ -244,28 +268,20 @@ static int rms_check(const char *who, int64_t rows, int C, int dtype, const void
 }
 
 int mmi_rmsnorm_fwd(const void *x, const float *w, void *y, int64_t rows, int C, int64_t x_ld, int64_t y_ld, float eps, int dtype,
-                    void *stream) {
+                    int y_dtype, void *stream) {
     if (!x || !w || !y) { set_error("mmi_rmsnorm_fwd: null pointer"); return MMI_ERR_ARG; }
-    if (int e = rms_check("mmi_rmsnorm_fwd", rows, C, dtype, x, y, x_ld, y_ld)) return e;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    switch (dtype) {
-        case MMI_F32: return rms_launch_t<float>(false, x, w, nullptr, y, nullptr, rows, C, x_ld, 0, y_ld, eps, st);
-        case MMI_BF16: return rms_launch_t<__nv_bfloat16>(false, x, w, nullptr, y, nullptr, rows, C, x_ld, 0, y_ld, eps, st);
-        default: return rms_launch_t<__half>(false, x, w, nullptr, y, nullptr, rows, C, x_ld, 0, y_ld, eps, st);
-    }
+    if (y_dtype < 0) y_dtype = dtype;
+    if (int e = rms_check("mmi_rmsnorm_fwd", rows, C, dtype, y_dtype, x, y, x_ld, y_ld)) return e;
+    return rms_dispatch(false, x, w, nullptr, y, nullptr, rows, C, x_ld, 0, y_ld, eps, dtype, y_dtype, static_cast<cudaStream_t>(stream));
 }
 
 int mmi_rmsnorm_bwd(const void *x, const float *w, const void *dy, void *dx, float *dw, int64_t rows, int C, int64_t x_ld,
-                    int64_t dy_ld, int64_t dx_ld, float eps, int dtype, void *stream) {
+                    int64_t dy_ld, int64_t dx_ld, float eps, int dtype, int dy_dtype, void *stream) {
     if (!x || !w || !dy || !dx || !dw) { set_error("mmi_rmsnorm_bwd: null pointer"); return MMI_ERR_ARG; }
-    if (int e = rms_check("mmi_rmsnorm_bwd", rows, C, dtype, x, dx, x_ld, dx_ld)) return e;
-    if ((dy_ld * (dtype == MMI_F32 ? 4 : 2)) % 16 || (reinterpret_cast<uintptr_t>(dy) & 15)) { set_error("mmi_rmsnorm_bwd: dy rows must be 16-byte aligned"); return MMI_ERR_ARG; }
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    switch (dtype) {
-        case MMI_F32: return rms_launch_t<float>(true, x, w, dy, dx, dw, rows, C, x_ld, dy_ld, dx_ld, eps, st);
-        case MMI_BF16: return rms_launch_t<__nv_bfloat16>(true, x, w, dy, dx, dw, rows, C, x_ld, dy_ld, dx_ld, eps, st);
-        default: return rms_launch_t<__half>(true, x, w, dy, dx, dw, rows, C, x_ld, dy_ld, dx_ld, eps, st);
-    }
+    if (dy_dtype < 0) dy_dtype = dtype;
+    if (int e = rms_check("mmi_rmsnorm_bwd", rows, C, dtype, dtype, x, dx, x_ld, dx_ld)) return e;
+    if (int e = rms_check("mmi_rmsnorm_bwd", rows, C, dtype, dy_dtype, x, dy, x_ld, dy_ld)) return e;
+    return rms_dispatch(true, x, w, dy, dx, dw, rows, C, x_ld, dy_ld, dx_ld, eps, dtype, dy_dtype, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -174,7 +174,7 @@ def causal_conv1d_silu(x, weight, bias=None, silu: bool = True):
 
 class _RMSNorm(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, eps):
+    def forward(ctx, x, weight, eps, out_dtype):
         global launches
         lib = _lib.load()
         _require_cuda(x, "rmsnorm")
@@ -183,12 +183,12 @@ class _RMSNorm(torch.autograd.Function):
         if x2.stride(1) != 1 or (x2.stride(0) * x2.element_size()) % 16 or x2.data_ptr() % 16:
             x2 = x2.contiguous()
         w = weight.detach().float().contiguous()
-        y = torch.empty((x2.shape[0], C), dtype=x.dtype, device=x.device)
+        y = torch.empty((x2.shape[0], C), dtype=out_dtype, device=x.device)
         _lib.check(lib.mmi_rmsnorm_fwd(_ptr(x2), _ptr(w), _ptr(y), x2.shape[0], C, x2.stride(0), y.stride(0), float(eps),
-                                       _DT[x.dtype], _stream(x)), "mmi_rmsnorm_fwd")
+                                       _DT[x.dtype], _DT[out_dtype], _stream(x)), "mmi_rmsnorm_fwd")
         launches += 1
         ctx.save_for_backward(x2, w)
-        ctx.eps, ctx.shape, ctx.wdtype = eps, x.shape, weight.dtype
+        ctx.eps, ctx.shape, ctx.wdtype, ctx.out_dtype = eps, x.shape, weight.dtype, out_dtype
         return y.view(x.shape)
 
     @staticmethod
@@ -197,22 +197,30 @@ class _RMSNorm(torch.autograd.Function):
         lib = _lib.load()
         x2, w = ctx.saved_tensors
         C = x2.shape[1]
-        g = dy.to(x2.dtype).reshape(-1, C)
+        g = dy.to(ctx.out_dtype).reshape(-1, C)  # arrives in the output's dtype: read as is, no cast pass
         if g.stride(1) != 1 or (g.stride(0) * g.element_size()) % 16 or g.data_ptr() % 16:
             g = g.contiguous()
         dx = torch.empty((x2.shape[0], C), dtype=x2.dtype, device=x2.device)
         dw = torch.empty(C, dtype=torch.float32, device=x2.device)
         _lib.check(lib.mmi_rmsnorm_bwd(_ptr(x2), _ptr(w), _ptr(g), _ptr(dx), _ptr(dw), x2.shape[0], C, x2.stride(0), g.stride(0),
-                                       dx.stride(0), float(ctx.eps), _DT[x2.dtype], _stream(x2)), "mmi_rmsnorm_bwd")
+                                       dx.stride(0), float(ctx.eps), _DT[x2.dtype], _DT[ctx.out_dtype], _stream(x2)),
+                   "mmi_rmsnorm_bwd")
         launches += 1
-        return dx.view(ctx.shape), dw.to(ctx.wdtype), None
+        return dx.view(ctx.shape), dw.to(ctx.wdtype), None, None
 
 
 def rmsnorm(x, weight, eps: float = 1e-5):
     """RMSNorm.forward of models/mamba.py:356-366 as one kernel per direction (x: (..., C), weight: (C))."""
     if x.dtype not in _DT:
         x = x.float()
-    return _RMSNorm.apply(x, weight, eps)
+    out_dtype = x.dtype
+    if x.dtype == torch.float32 and torch.is_autocast_enabled():
+        # autocast runs norms in fp32 and casts their output for the 16-bit GEMM that follows: emit that dtype directly
+        # (one rounding either way) and take the 16-bit gradient as it comes -- two cast passes over (B, L, C) saved
+        ac = torch.get_autocast_gpu_dtype()
+        if ac in (torch.bfloat16, torch.float16):
+            out_dtype = ac
+    return _RMSNorm.apply(x, weight, eps, out_dtype)
 
 
 def _tok_gather(rgb, ir):

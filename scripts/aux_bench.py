@@ -97,7 +97,7 @@ for dt in (torch.float32, torch.bfloat16):
     dx2, dw2 = torch.empty_like(x2), torch.empty(C, device=dev)
     w32 = wr.detach().float()
     t = timeit(lambda: lib.mmi_rmsnorm_bwd(P(x2), P(w32), P(g2), P(dx2), P(dw2), x2.shape[0], C, x2.stride(0), g2.stride(0),
-                                           dx2.stride(0), 1e-5, DT[dt], ST(x2)), 20)
+                                           dx2.stride(0), 1e-5, DT[dt], -1, ST(x2)), 20)
     report(f"RMSNorm bwd kernel only {tag}", t, 3 * Bt * Lt * C * es)
     xc2, gy2 = xc.detach(), gy
     dxc, dwc, dbc = torch.empty_like(xc2), torch.empty(EDt, 4, device=dev), torch.empty(EDt, device=dev)

@@ -20,7 +20,7 @@ gy, dxc = torch.randn_like(xc), torch.empty_like(xc)
 wc, bc = torch.randn(ED, 4, device="cuda"), torch.randn(ED, device="cuda")
 dwc, dbc = torch.empty(ED, 4, device="cuda"), torch.empty(ED, device="cuda")
 for _ in range(3):
-    lib.mmi_rmsnorm_bwd(P(x2), P(w32), P(g2), P(dx2), P(dw2), x2.shape[0], C, x2.stride(0), g2.stride(0), dx2.stride(0), 1e-5, DT[dt], ST(x2))
+    lib.mmi_rmsnorm_bwd(P(x2), P(w32), P(g2), P(dx2), P(dw2), x2.shape[0], C, x2.stride(0), g2.stride(0), dx2.stride(0), 1e-5, DT[dt], -1, ST(x2))
     lib.mmi_causal_conv1d_bwd(P(xc), P(wc), P(bc), P(gy), P(dxc), P(dwc), P(dbc), Bt, Lt, ED, 4, xc.stride(1), gy.stride(1), dxc.stride(1),
                               DT[dt], 1, ST(xc))
 torch.cuda.synchronize()

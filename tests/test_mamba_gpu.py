@@ -149,6 +149,28 @@ def test_rmsnorm_vs_torch_fp64(rows, C, dtype, tol):
     assert relerr(gw.float().cpu().numpy(), gwr.cpu().numpy()) <= max(tol, 5e-5)
 
 
+@pytest.mark.parametrize("ac", [torch.bfloat16, torch.float16])
+def test_rmsnorm_under_autocast_emits_gemm_dtype(ac):
+    """under autocast an fp32 input gives the 16-bit tensor the following GEMM would cast to -- bit-identical to the fp32
+    result followed by .to(ac) -- and the backward takes the 16-bit gradient directly (dx, dw in fp32)."""
+    from mmidet_b200 import ops
+    torch.manual_seed(9)
+    rows, C = 300, 256
+    x = torch.randn(2, rows, C, device="cuda", requires_grad=True)
+    w = (torch.rand(C, device="cuda") + 0.5).requires_grad_(True)
+    g = torch.randn(2, rows, C, device="cuda").to(ac)
+    y32 = ops.rmsnorm(x, w, 1e-5)
+    with torch.autocast("cuda", dtype=ac):
+        y = ops.rmsnorm(x, w, 1e-5)
+    assert y.dtype == ac and y32.dtype == torch.float32
+    assert torch.equal(y, y32.detach().to(ac))
+    gx, gw = torch.autograd.grad(y, [x, w], g)
+    gx32, gw32 = torch.autograd.grad(y32, [x, w], g.float())
+    assert gx.dtype == torch.float32 and gw.dtype == torch.float32
+    assert relerr(gx.cpu().numpy(), gx32.cpu().numpy()) <= 1e-5
+    assert relerr(gw.cpu().numpy(), gw32.cpu().numpy()) <= 5e-5
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("shape", [(2, 16, 6, 5), (1, 72, 7, 9), (3, 256, 20, 20), (2, 136, 12, 14), (1, 8, 4, 4),
                                    (2, 64, 80, 80), (1, 200, 16, 17)])  # 16-byte-vector path with partial tiles, and scalar path
