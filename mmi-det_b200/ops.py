@@ -210,7 +210,8 @@ class _RMSNorm(torch.autograd.Function):
 
 
 def rmsnorm(x, weight, eps: float = 1e-5):
-    """RMSNorm.forward of models/mamba.py:356-366 as one kernel per direction (x: (..., C), weight: (C))."""
+    """RMSNorm.forward of models/mamba.py:356-366 as one kernel per direction (x: (..., C), weight: (C)).
+    Under torch.autocast an fp32 input returns the autocast dtype (what the GEMM consuming it would cast to; same bits)."""
     if x.dtype not in _DT:
         x = x.float()
     out_dtype = x.dtype
