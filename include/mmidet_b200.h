@@ -127,6 +127,8 @@ int mmi_separation_loss(const float *M, float *loss, int l, int K, void *stream)
  *   loss (nullable) fp32[1] = Seperation_loss(rows) (models/common.py:494).  hm = high * fea is needed only for the
  *   first ceil(B / 8) batch entries (len // 8 rows reach the loss, common.py:487); the call computes it into ws.
  *   Three launches: high-pass product (both modalities), pattern kernel (grid B x 2), separation loss.
+ *   ws == NULL selects the sibling module GPT1.forward (models/common.py:196-239), which has no Fourier branch: the two
+ *   high-pass row blocks are not produced and the loss runs over rows[:16B] = [M_vis; M_ir].
  * The backward differentiates the token path (the reference detaches the pattern loss, models/yolo_test.py:230):
  *   dtok (B, 2P, C) dtype -> dfea_vis, dfea_ir (B, C, P) dtype, dW1 (8, C), dW2 (C, 8) fp32 (overwritten; summed in a
  *   fixed order from per-CTA partials in ws).  rows is the forward's output.

@@ -234,7 +234,7 @@ int64_t mmi_ffm_pattern_ws_bytes(int B, int C, int P) { return B > 0 && C > 0 &&
 
 int mmi_ffm_pattern_fwd(const void *fea_vis, const void *fea_ir, const float *W1, const float *W2, void *tok, float *rows,
                         float *loss, void *ws, int B, int C, int H, int W, int dtype, void *stream) {
-    if (!fea_vis || !fea_ir || !W1 || !W2 || !tok || !rows || !ws) { set_error("mmi_ffm_pattern_fwd: null pointer"); return MMI_ERR_ARG; }
+    if (!fea_vis || !fea_ir || !W1 || !W2 || !tok || !rows) { set_error("mmi_ffm_pattern_fwd: null pointer"); return MMI_ERR_ARG; }
     if (H < 1 || W < 1) { set_error("mmi_ffm_pattern_fwd: pooled map %dx%d", H, W); return MMI_ERR_ARG; }
     if (!elem_size(dtype)) { set_error("mmi_ffm_pattern_fwd: unknown dtype %d", dtype); return MMI_ERR_ARG; }
     if (int e = require_device()) return e;

@@ -222,10 +222,12 @@ int64_t ffm_pattern_ws_bytes(int B, int C, int P) {
 
 int ffm_pattern_fwd_launch(const void *fea_vis, const void *fea_ir, const float *W1, const float *W2, void *tok, float *rows,
                            float *loss, float *ws, int B, int C, int H, int W, int dtype, cudaStream_t st) {
-    const int P = H * W, nbh = (B + 7) / 8;
+    // ws == nullptr: no high-pass branch (GPT1.forward, models/common.py:218-239: rows = [M_vis; M_ir], 16B of them)
+    const int P = H * W, nbh = ws ? (B + 7) / 8 : 0;
     if (int e = check_pattern("mmi_ffm_pattern_fwd", B, C, P)) return e;
-    float *hm_vis = ws, *hm_ir = ws + int64_t(nbh) * C * P;
-    if (int e = ffm_highmul_pair_launch(fea_vis, fea_ir, hm_vis, hm_ir, nbh * C, H, W, dtype, st)) return e;
+    float *hm_vis = ws, *hm_ir = ws ? ws + int64_t(nbh) * C * P : nullptr;
+    if (nbh)
+        if (int e = ffm_highmul_pair_launch(fea_vis, fea_ir, hm_vis, hm_ir, nbh * C, H, W, dtype, st)) return e;
     const size_t smem = (size_t(kPatJ + kPatCT) * (P + 1) + kPatJ * kPatThreads) * sizeof(float);
     const dim3 grid(B, 2);
 #define MMI_PAT_FWD(T)                                                                                                  \
@@ -239,7 +241,7 @@ int ffm_pattern_fwd_launch(const void *fea_vis, const void *fea_ir, const float 
     }
 #undef MMI_PAT_FWD
     if (int e = check_cuda(cudaGetLastError(), "ffm_pattern_fwd launch")) return e;
-    return loss ? separation_loss_launch(rows, loss, 18 * B, P, st) : MMI_OK;
+    return loss ? separation_loss_launch(rows, loss, (ws ? 18 : 16) * B, P, st) : MMI_OK;
 }
 
 int ffm_pattern_bwd_launch(const void *fea_vis, const void *fea_ir, const void *dtok, const float *rows, const float *W1,

@@ -65,28 +65,28 @@ def separation_loss(M: torch.Tensor) -> torch.Tensor:
 Seperation_loss = separation_loss  # the reference's spelling (models/common.py:128)
 
 
-def _pattern_fwd(vis, ir, w1, w2):
+def _pattern_fwd(vis, ir, w1, w2, high=True):
     lib = _lib.load()
     B, C, H, W = vis.shape
     tok = torch.empty((B, 2 * H * W, C), dtype=vis.dtype, device=vis.device)
     rows = torch.empty((18 * B, H * W), dtype=torch.float32, device=vis.device)
     loss = torch.empty(1, dtype=torch.float32, device=vis.device)
-    ws = torch.empty(lib.mmi_ffm_pattern_ws_bytes(B, C, H * W), dtype=torch.uint8, device=vis.device)
+    ws = torch.empty(lib.mmi_ffm_pattern_ws_bytes(B, C, H * W), dtype=torch.uint8, device=vis.device) if high else None
     _lib.check(lib.mmi_ffm_pattern_fwd(_ops._ptr(vis), _ops._ptr(ir), _ops._ptr(w1), _ops._ptr(w2), _ops._ptr(tok),
                                        _ops._ptr(rows), _ops._ptr(loss), _ops._ptr(ws), B, C, H, W, _ops._DT[vis.dtype],
                                        _ops._stream(vis)), "mmi_ffm_pattern_fwd")
-    _ops.launches += 3
+    _ops.launches += 3 if high else 2
     return tok, rows, loss[0]
 
 
 class _PatternTokens(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, vis, ir, conv1_w, conv2_w):
+    def forward(ctx, vis, ir, conv1_w, conv2_w, high):
         C = vis.shape[1]
         w1 = conv1_w.detach().reshape(8, C).float().contiguous()
         w2 = conv2_w.detach().reshape(C, 8).float().contiguous()
         vis, ir = vis.contiguous(), ir.contiguous()
-        tok, rows, loss = _pattern_fwd(vis, ir, w1, w2)
+        tok, rows, loss = _pattern_fwd(vis, ir, w1, w2, high)
         ctx.save_for_backward(vis, ir, w1, w2, rows)
         ctx.wshape = (conv1_w.shape, conv2_w.shape, conv1_w.dtype, conv2_w.dtype)
         ctx.mark_non_differentiable(loss)
@@ -108,12 +108,13 @@ class _PatternTokens(torch.autograd.Function):
                    "mmi_ffm_pattern_bwd")
         _ops.launches += 2
         s1, s2, d1, d2 = ctx.wshape
-        return dvis, dir_, dw1.reshape(s1).to(d1), dw2.reshape(s2).to(d2)
+        return dvis, dir_, dw1.reshape(s1).to(d1), dw2.reshape(s2).to(d2), None
 
 
-def pattern_tokens(vis: torch.Tensor, ir: torch.Tensor, conv1_weight: torch.Tensor, conv2_weight: torch.Tensor):
+def pattern_tokens(vis: torch.Tensor, ir: torch.Tensor, conv1_weight: torch.Tensor, conv2_weight: torch.Tensor, high: bool = True):
     """Pattern path of GPT1_fourier.forward (models/common.py:440-516) on the pooled maps vis, ir (B, C, h, w):
     -> (token_embeddings (B, 2hw, C), pattenLoss 0-d fp32).  conv1_weight (8, C, 1, 1), conv2_weight (C, 8, 1, 1).
+    high=False: the same path of GPT1.forward (models/common.py:218-262), which has no Fourier branch (loss over 16B rows).
     Gradients flow through the tokens to vis, ir and both weights; the loss is a value only (the reference detaches
     it, models/yolo_test.py:230)."""
     if not (vis.is_cuda and ir.is_cuda):
@@ -124,7 +125,20 @@ def pattern_tokens(vis: torch.Tensor, ir: torch.Tensor, conv1_weight: torch.Tens
         raise ValueError("pattern_tokens: conv1 must map C -> 8 and conv2 8 -> C (models/common.py:330-336)")
     if vis.dtype not in _ops._DT:
         vis = vis.float()
-    return _PatternTokens.apply(vis, ir.to(vis.dtype), conv1_weight, conv2_weight)
+    return _PatternTokens.apply(vis, ir.to(vis.dtype), conv1_weight, conv2_weight, bool(high))
+
+
+def _focus_forward(self, x, high):
+    rgb_fea, ir_fea = x[0], x[1]
+    assert rgb_fea.shape[0] == ir_fea.shape[0]
+    bs, c, h, w = rgb_fea.shape
+    anchors = (self.vert_anchors, self.horz_anchors)
+    tok, self.pattenLoss = pattern_tokens(_ops.adaptive_avg_pool(rgb_fea, anchors), _ops.adaptive_avg_pool(ir_fea, anchors),
+                                          self.conv1.weight, self.conv2.weight, high=high)
+    t = self.drop(self.pos_emb + tok)
+    t = self.ln_f(self.trans_blocks(t))
+    rgb_out, ir_out = _ops.tokens_scatter(t, (bs, self.n_embd, self.vert_anchors, self.horz_anchors))
+    return _ops.upsample_bilinear(rgb_out, (h, w)), _ops.upsample_bilinear(ir_out, (h, w)), self.pattenLoss
 
 
 def fourier_forward(self, x):
@@ -134,13 +148,10 @@ def fourier_forward(self, x):
     (ops.adaptive_avg_pool / upsample_bilinear); the Fourier split, both conv1+sigmoid branches, the separation loss,
     conv2 * fea and the token layout are pattern_tokens; tokens go back to two maps with the token-scatter kernel.
     Returns (rgb_fea_out, ir_fea_out, pattenLoss) and sets self.pattenLoss like the reference."""
-    rgb_fea, ir_fea = x[0], x[1]
-    assert rgb_fea.shape[0] == ir_fea.shape[0]
-    bs, c, h, w = rgb_fea.shape
-    anchors = (self.vert_anchors, self.horz_anchors)
-    tok, self.pattenLoss = pattern_tokens(_ops.adaptive_avg_pool(rgb_fea, anchors), _ops.adaptive_avg_pool(ir_fea, anchors),
-                                          self.conv1.weight, self.conv2.weight)
-    t = self.drop(self.pos_emb + tok)
-    t = self.ln_f(self.trans_blocks(t))
-    rgb_out, ir_out = _ops.tokens_scatter(t, (bs, self.n_embd, self.vert_anchors, self.horz_anchors))
-    return _ops.upsample_bilinear(rgb_out, (h, w)), _ops.upsample_bilinear(ir_out, (h, w)), self.pattenLoss
+    return _focus_forward(self, x, True)
+
+
+def gpt1_forward(self, x):
+    """Replacement for GPT1.forward (models/common.py:196-298), the sibling of GPT1_fourier without the Fourier branch:
+    same pooling / pattern path / transformer / upsample, separation loss over [M_vis; M_ir] only (:218-239)."""
+    return _focus_forward(self, x, False)

@@ -223,7 +223,8 @@ def install(ref_models=None, scan=True, pscan=True, ffm=True, fusion=False):
 
     scan    MambaBlock.selective_scan / selective_scan_seq  -> fused kernel (class attribute patch; ctor untouched)
     pscan   models.mamba.pscan (= PScan.apply)               -> mmidet_b200.pscan.pscan
-    ffm     models.common.extract_frequency2, Seperation_loss -> mmidet_b200.ffm; GPT1_fourier.forward -> ffm.fourier_forward
+    ffm     models.common.extract_frequency2, Seperation_loss -> mmidet_b200.ffm; GPT1_fourier.forward -> ffm.fourier_forward,
+            GPT1.forward -> ffm.gpt1_forward
             (class attribute patch: the module keeps its ctor, parameters and state_dict)
     fusion  models.yolo_test.GPT                              -> MambaFusion (YAML rows naming GPT then build it)
     Returns the list of replaced attributes so a caller can restore them."""
@@ -254,6 +255,8 @@ def install(ref_models=None, scan=True, pscan=True, ffm=True, fusion=False):
         swap(mc, "Seperation_loss", _ffm.separation_loss)
         if hasattr(mc, "GPT1_fourier"):
             swap(mc.GPT1_fourier, "forward", _ffm.fourier_forward)
+        if hasattr(mc, "GPT1"):
+            swap(mc.GPT1, "forward", _ffm.gpt1_forward)
     if fusion:
         swap(mod("models.yolo_test"), "GPT", MambaFusion)
     return saved

@@ -395,8 +395,9 @@ def upsample_bilinear(x, size):
     return top * (1 - ly)[:, None] + bot * ly[:, None]
 
 
-def ffm_pattern(pool_vis, pool_ir, conv1_w, conv2_w):
-    """models/common.py:434-516 (GPT1_fourier.forward between avgpool and the transformer), literally:
+def ffm_pattern(pool_vis, pool_ir, conv1_w, conv2_w, high=True):
+    """models/common.py:434-516 (GPT1_fourier.forward between avgpool and the transformer), literally
+    (high=False: GPT1.forward, models/common.py:218-262 -- no Fourier branch, loss over [M_vis; M_ir]):
     pooled maps (B, C, h, w), conv1_w (8, C), conv2_w (C, 8) -> (token_embeddings (B, 2hw, C), pattenLoss).
     1x1 convolutions are einsums over the channel axis; `.view(-1, h*w)` flattens (b, j) row-major."""
     B, Cc, h, w = pool_vis.shape
@@ -404,8 +405,8 @@ def ffm_pattern(pool_vis, pool_ir, conv1_w, conv2_w):
     conv1 = lambda t: np.einsum("jc,bchw->bjhw", conv1_w.astype(np.float64), t.astype(np.float64))  # noqa: E731
     rows_high, rows, toks = [], [], []
     for fea in (pool_vis, pool_ir):
-        _, high = extract_frequency2(fea)                                   # :434-435
-        high_multi = high.astype(np.float32) * fea                          # :440-441 (fp16 * fp32 -> fp32)
+        _, hi_pass = extract_frequency2(fea)                                # :434-435
+        high_multi = hi_pass.astype(np.float32) * fea                       # :440-441 (fp16 * fp32 -> fp32)
         rows_high.append(sig(conv1(high_multi)).reshape(-1, h * w))         # :444-455
         M = sig(conv1(fea))                                                 # :476-480
         rows.append(M.reshape(-1, h * w))                                   # :482-483
@@ -413,6 +414,8 @@ def ffm_pattern(pool_vis, pool_ir, conv1_w, conv2_w):
         toks.append((PT * fea).reshape(B, Cc, -1))                          # :499-503
     n_half = len(rows_high[0]) // 8                                         # :487
     cat = np.concatenate([rows[0], rows[1], rows_high[0][:n_half], rows_high[1][:n_half]], axis=0)  # :488-489
+    if not high:
+        cat = np.concatenate([rows[0], rows[1]], axis=0)                    # GPT1: models/common.py:233-235
     loss = separation_loss(cat)                                             # :494
     tok = np.concatenate(toks, axis=2).transpose(0, 2, 1)                   # :514-519
     return np.ascontiguousarray(tok), loss

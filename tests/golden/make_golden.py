@@ -185,9 +185,11 @@ def gen_pattern():
     """GPT1_fourier.forward (common.py:357-552) with the transformer stack emptied (n_layer=0: pooling, Fourier split,
     pattern maps, Seperation_loss, conv2 * fea, tokens, pos_emb, ln_f, upsample remain) -- outputs, the token
     embeddings entering self.drop, and gradients of a seeded linear functional of the two output maps."""
-    for name, (B, Cc, H, W, seed) in {"pattern_b2": (2, 64, 12, 10, 0), "pattern_b9": (9, 16, 9, 11, 1)}.items():
+    cases = {"pattern_b2": (2, 64, 12, 10, 0, C.GPT1_fourier), "pattern_b9": (9, 16, 9, 11, 1, C.GPT1_fourier),
+             "pattern_gpt1": (3, 32, 11, 9, 2, C.GPT1)}  # GPT1 (common.py:140-298): same module without the Fourier branch
+    for name, (B, Cc, H, W, seed, cls) in cases.items():
         torch.manual_seed(seed)
-        m = C.GPT1_fourier(Cc, n_layer=0).eval()
+        m = cls(Cc, n_layer=0).eval()
         with torch.no_grad():
             m.pos_emb.normal_(0, 0.5)
             m.ln_f.weight.uniform_(0.5, 1.5)
@@ -204,7 +206,7 @@ def gen_pattern():
         ro, io, loss = m([vis, ir])
         hk.remove(), hp.remove()
         ((ro * g1).sum() + (io * g2).sum()).backward()
-        print(name, "loss", float(loss), "rows", 18 * B)
+        print(name, "loss", float(loss))
         save(name, vis=vis, ir=ir, g1=g1, g2=g2, conv1_w=m.conv1.weight, conv2_w=m.conv2.weight, pos_emb=m.pos_emb,
              ln_w=m.ln_f.weight, ln_b=m.ln_f.bias, pool_vis=pooled[0], pool_ir=pooled[1], drop_in=cap["drop_in"],
              rgb_out=ro, ir_out=io, loss=loss.detach().reshape(1), d_vis=vis.grad, d_ir=ir.grad,

@@ -17,8 +17,12 @@ def _fake_tree():
         def forward(self, x):
             return "ref_fourier"
 
+    class GPT1:  # models/common.py:140
+        def forward(self, x):
+            return "ref_gpt1"
+
     mamba = types.SimpleNamespace(MambaBlock=MambaBlock, pscan="ref_pscan")
-    common = types.SimpleNamespace(extract_frequency2="ref_ffm", Seperation_loss="ref_sep", GPT1_fourier=GPT1_fourier)
+    common = types.SimpleNamespace(extract_frequency2="ref_ffm", Seperation_loss="ref_sep", GPT1_fourier=GPT1_fourier, GPT1=GPT1)
     yolo = types.SimpleNamespace(GPT="ref_gpt")
     return types.SimpleNamespace(mamba=mamba, common=common, yolo_test=yolo)
 
@@ -31,6 +35,7 @@ def test_install_and_uninstall():
     assert t.common.extract_frequency2 is ffm.extract_frequency2
     assert t.common.Seperation_loss is ffm.separation_loss
     assert t.common.GPT1_fourier.forward is ffm.fourier_forward
+    assert t.common.GPT1.forward is ffm.gpt1_forward
     assert t.yolo_test.GPT is M.MambaFusion
     assert t.mamba.MambaBlock.selective_scan is t.mamba.MambaBlock.selective_scan_seq
     # the patched method is the fused operator: CPU tensors must raise, never fall back
@@ -44,6 +49,7 @@ def test_install_and_uninstall():
     assert t.mamba.pscan == "ref_pscan" and t.yolo_test.GPT == "ref_gpt" and t.common.extract_frequency2 == "ref_ffm"
     assert t.mamba.MambaBlock().selective_scan() == "ref_scan"
     assert t.common.GPT1_fourier().forward(None) == "ref_fourier"
+    assert t.common.GPT1().forward(None) == "ref_gpt1"
 
 
 def test_state_dict_layout_matches_reference(golden):

@@ -110,12 +110,14 @@ def test_separation_loss_matches_reference(golden):
     assert abs(O.separation_loss(g["M"]) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
 
 
-@pytest.mark.parametrize("tag", ["b2", "b9"])
+@pytest.mark.parametrize("tag", ["b2", "b9", "gpt1"])
 def test_ffm_pattern_matches_reference(golden, tag):
-    """pattern path of GPT1_fourier.forward (common.py:434-516) vs tensors captured inside the unmodified reference."""
+    """pattern path of GPT1_fourier.forward (common.py:434-516) / GPT1.forward (:218-262) vs tensors captured inside the
+    unmodified reference."""
     g = golden(f"pattern_{tag}")
     C = g["pool_vis"].shape[1]
-    tok, loss = O.ffm_pattern(g["pool_vis"], g["pool_ir"], g["conv1_w"].reshape(8, C), g["conv2_w"].reshape(C, 8))
+    tok, loss = O.ffm_pattern(g["pool_vis"], g["pool_ir"], g["conv1_w"].reshape(8, C), g["conv2_w"].reshape(C, 8),
+                              high=tag != "gpt1")
     assert relerr(tok + g["pos_emb"], g["drop_in"]) <= 1e-5
     assert abs(loss - float(g["loss"][0])) <= 1e-5 * abs(float(g["loss"][0]))
 

@@ -105,12 +105,12 @@ def _pattern_torch(vis, ir, w1, w2):
     return torch.cat(toks, dim=2).transpose(1, 2)
 
 
-@pytest.mark.parametrize("tag", ["b2", "b9"])
+@pytest.mark.parametrize("tag", ["b2", "b9", "gpt1"])
 def test_pattern_tokens_vs_reference_golden(golden, tag):
-    """tokens entering self.drop and pattenLoss captured inside the unmodified GPT1_fourier.forward."""
+    """tokens entering self.drop and pattenLoss captured inside the unmodified GPT1_fourier.forward / GPT1.forward."""
     from mmidet_b200.ffm import pattern_tokens
     g = golden(f"pattern_{tag}")
-    tok, loss = pattern_tokens(_t(g["pool_vis"]), _t(g["pool_ir"]), _t(g["conv1_w"]), _t(g["conv2_w"]))
+    tok, loss = pattern_tokens(_t(g["pool_vis"]), _t(g["pool_ir"]), _t(g["conv1_w"]), _t(g["conv2_w"]), high=tag != "gpt1")
     assert tok.shape == g["drop_in"].shape and loss.dim() == 0 and not loss.requires_grad
     assert relerr(tok.cpu().numpy() + g["pos_emb"], g["drop_in"]) <= 1e-5
     assert abs(float(loss) - float(g["loss"][0])) <= 1e-5 * abs(float(g["loss"][0]))
@@ -138,11 +138,12 @@ class _FourierStandIn(torch.nn.Module):
             self.conv2.weight.copy_(torch.from_numpy(g["conv2_w"]))
 
 
-@pytest.mark.parametrize("tag", ["b2", "b9"])
+@pytest.mark.parametrize("tag", ["b2", "b9", "gpt1"])
 def test_fourier_forward_vs_reference_golden(golden, tag):
     """the replacement bound onto GPT1_fourier.forward: both output maps, the loss and the gradients of a seeded
     functional of the outputs w.r.t. both inputs, conv1, conv2 and pos_emb -- all from the unmodified reference."""
-    from mmidet_b200.ffm import fourier_forward
+    from mmidet_b200 import ffm
+    fourier_forward = ffm.gpt1_forward if tag == "gpt1" else ffm.fourier_forward  # GPT1: the sibling without the Fourier branch
     g = golden(f"pattern_{tag}")
     m = _FourierStandIn(g).cuda().eval()
     vis, ir = _t(g["vis"]).requires_grad_(True), _t(g["ir"]).requires_grad_(True)
