@@ -286,10 +286,10 @@ __global__ void __launch_bounds__(kRsThreads, 3)
     }
 }
 
-// Same map when two whole images fit in shared memory (160 x 160 fp32 does): the CTA streams its images through a
-// two-slot ring filled by 1-D bulk copies (cp.async.bulk, one mbarrier per slot), so the next image is in flight while
-// the current one is reduced out of shared memory -- the per-image tail no longer idles the memory system.  Vertical
-// taps first (thread = anchor row x four columns, 16-byte shared loads), then the horizontal taps as above.
+// Same map for images of 32 KB and more: one CTA per SM streams its images, cut into row bands, through a four-slot
+// shared-memory ring filled by 1-D bulk copies (cp.async.bulk, one mbarrier per slot), so three bands are in flight
+// while one is reduced out of shared memory -- the per-image tail no longer idles the memory system.  Vertical taps
+// first (thread = anchor row x four columns, 16-byte shared loads), then the horizontal taps as above.
 __device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
@@ -298,10 +298,14 @@ __device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_
 
 constexpr int kRingThreads = 512;  // measured: 256 threads 0.060 ms (bilinear), 512 0.053 ms, 1024 with split supports 0.072 ms
 
+constexpr int kRingSlots = 4;
+
+// Units of work are row bands (NH per image, RBn rows each): with four slots three bands are in flight while one is
+// reduced, which is what keeps one CTA per SM close to its share of the HBM bandwidth.
 template <typename T>
 __global__ void __launch_bounds__(kRingThreads, 1)
     resample_reduce_ring_kernel(const T *__restrict__ big, T *__restrict__ small, int BC, int H, int W, int hs, int ws,
-                                int mode, int R) {
+                                int mode, int NH, int RBn, uint32_t slot_stride) {
     extern __shared__ __align__(128) float sm[];
     float *p = sm;
     TapTable tx, ty;
@@ -310,14 +314,17 @@ __global__ void __launch_bounds__(kRingThreads, 1)
     int *xlo = reinterpret_cast<int *>(p), *xhi = xlo + ws, *ylo = xhi + ws, *yhi = ylo + hs;
     p += 2 * ws + 2 * hs;
     p = sm + (((p - sm) + 3) & ~3);
-    float *V = p;  // [R][hs][W]: vertical sums, the anchor row's support split into R parts
-    p += R * hs * W;
+    float *V = p;  // [hs][W]: vertical sums of the current image, accumulated band by band
+    p += hs * W;
+    float *WY = p;  // [hs][H] and [ws][W]: dense tap weights (image-independent, built once), so that the inner loops
+    p += hs * H;    // are one broadcast weight load + one data load + FMAs
+    float *WX = p;
+    p += ws * W;
+    p = sm + (((p - sm) + 3) & ~3);
     uint64_t *full = reinterpret_cast<uint64_t *>(p);
-    p += 4;
+    p += 2 * kRingSlots;
     p = sm + (((p - sm) + 31) & ~31);  // 128-byte aligned slots
-    const uint32_t img_bytes = uint32_t(H) * W * sizeof(T);
     unsigned char *slot0 = reinterpret_cast<unsigned char *>(p);
-    const uint32_t slot_stride = (img_bytes + 127u) & ~127u;
     const int tid = threadIdx.x, W4 = W >> 2;
 
     for (int i = tid; i < W; i += kRingThreads) taps(mode, i, W, ws, tx.t[i].i0, tx.t[i].i1, tx.t[i].w0, tx.t[i].w1);
@@ -325,8 +332,7 @@ __global__ void __launch_bounds__(kRingThreads, 1)
     for (int j = tid; j < ws; j += kRingThreads) xlo[j] = 0, xhi[j] = -1;
     for (int a = tid; a < hs; a += kRingThreads) ylo[a] = 0, yhi[a] = -1;
     if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
+        for (int i = 0; i < kRingSlots; ++i) mbar_init(&full[i], 1);
         fence_mbar_init();
     }
     __syncthreads();
@@ -341,51 +347,73 @@ __global__ void __launch_bounds__(kRingThreads, 1)
     };
     for (int x = tid; x < W; x += kRingThreads) ends(tx, W, xlo, xhi, x);
     for (int y = tid; y < H; y += kRingThreads) ends(ty, H, ylo, yhi, y);
-    if (tid == 0 && int(blockIdx.x) < BC) {
-        mbar_arrive_expect_tx(&full[0], img_bytes);
-        bulk_load_1d(slot0, big + int64_t(blockIdx.x) * H * W, img_bytes, &full[0]);
-    }
+    for (int i = tid; i < hs * H; i += kRingThreads) WY[i] = ty.weight(i % H, i / H);
+    for (int i = tid; i < ws * W; i += kRingThreads) WX[i] = tx.weight(i % W, i / W);
+
+    const int nimg = int(blockIdx.x) < BC ? (BC - 1 - int(blockIdx.x)) / int(gridDim.x) + 1 : 0;  // images of this CTA
+    const int nunit = nimg * NH;
+    auto issue = [&](int u) {  // unit u = band (u % NH) of this CTA's image (u / NH), into slot u % kRingSlots
+        const int im = blockIdx.x + (u / NH) * gridDim.x, y0 = (u % NH) * RBn;
+        const uint32_t bytes = uint32_t(min(RBn, H - y0)) * W * sizeof(T);
+        uint64_t *bar = &full[u % kRingSlots];
+        mbar_arrive_expect_tx(bar, bytes);
+        bulk_load_1d(slot0 + size_t(u % kRingSlots) * slot_stride, big + (int64_t(im) * H + y0) * W, bytes, bar);
+    };
+    if (tid == 0)
+        for (int u = 0; u < kRingSlots - 1 && u < nunit; ++u) issue(u);
     __syncthreads();
     const int parts = kRingThreads / (hs * ws) >= 32 ? 32 : (kRingThreads / (hs * ws) >= 16 ? 16 : (kRingThreads / (hs * ws) >= 8 ? 8 : 4));
-    int k = 0;
-    for (int im = blockIdx.x; im < BC; im += gridDim.x, ++k) {
-        const int nxt = im + gridDim.x;
-        if (tid == 0 && nxt < BC) {  // slot (k+1)&1 was drained before the barrier that ended iteration k-1
-            mbar_arrive_expect_tx(&full[(k + 1) & 1], img_bytes);
-            bulk_load_1d(slot0 + size_t((k + 1) & 1) * slot_stride, big + int64_t(nxt) * H * W, img_bytes, &full[(k + 1) & 1]);
-        }
-        mbar_wait(&full[k & 1], (k >> 1) & 1);
-        const T *img = reinterpret_cast<const T *>(slot0 + size_t(k & 1) * slot_stride);
-        for (int task = tid; task < R * hs * W4; task += kRingThreads) {
-            const int r = task / (hs * W4), a = (task / W4) % hs, q = task % W4;
+    for (int u = 0; u < nunit; ++u) {
+        // slot (u - 1) % kRingSlots was drained before the barrier that ended unit u - 1
+        if (tid == 0 && u + kRingSlots - 1 < nunit) issue(u + kRingSlots - 1);
+        const int band = u % NH, y0 = band * RBn, y1 = min(H, y0 + RBn);
+        mbar_wait(&full[u % kRingSlots], (u / kRingSlots) & 1);
+        const T *rowsp = reinterpret_cast<const T *>(slot0 + size_t(u % kRingSlots) * slot_stride) - int64_t(y0) * W;
+        for (int task = tid; task < hs * W4; task += kRingThreads) {  // the same thread owns V[a][4q..] in every band
+            const int a = task / W4, q = task % W4;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int lo = ylo[a], n = yhi[a] - lo + 1;
-            const int ya = lo + (n * r) / R, yb = lo + (n * (r + 1)) / R;
-            for (int y = ya; y < yb; ++y) {
-                const float w = ty.weight(y, a);
-                const float4 v = load4<T>(img + y * W + 4 * q);
+            if (band) acc = *reinterpret_cast<const float4 *>(V + a * W + 4 * q);
+            const int ya = max(ylo[a], y0), yb = min(yhi[a] + 1, y1);
+            const T *col = rowsp + 4 * q;
+            const float *wy = WY + a * H;
+            int y = ya;
+            for (; y + 4 <= yb; y += 4) {  // four rows at a time: the shared-memory loads of a group are independent
+                float w[4];
+                float4 v[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    w[i] = wy[y + i];
+                    v[i] = load4<T>(col + int64_t(y + i) * W);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    acc.x = fmaf(w[i], v[i].x, acc.x), acc.y = fmaf(w[i], v[i].y, acc.y), acc.z = fmaf(w[i], v[i].z, acc.z),
+                    acc.w = fmaf(w[i], v[i].w, acc.w);
+            }
+            for (; y < yb; ++y) {
+                const float w = wy[y];
+                const float4 v = load4<T>(col + int64_t(y) * W);
                 acc.x = fmaf(w, v.x, acc.x), acc.y = fmaf(w, v.y, acc.y), acc.z = fmaf(w, v.z, acc.z), acc.w = fmaf(w, v.w, acc.w);
             }
-            *reinterpret_cast<float4 *>(V + (r * hs + a) * W + 4 * q) = acc;
+            *reinterpret_cast<float4 *>(V + a * W + 4 * q) = acc;
         }
-        __syncthreads();
-        T *dst = small + int64_t(im) * hs * ws;
-        for (int c0 = 0; c0 < hs * ws; c0 += kRingThreads / parts) {
-            const int cell = c0 + tid / parts, part = tid % parts;
-            float sacc = 0.f;
-            int a = 0, j = 0;
-            if (cell < hs * ws) {
-                a = cell / ws, j = cell % ws;
-                for (int x = xlo[j] + part; x <= xhi[j]; x += parts) {
-                    float v = V[a * W + x];
-                    for (int r = 1; r < R; ++r) v += V[(r * hs + a) * W + x];
-                    sacc = fmaf(tx.weight(x, j), v, sacc);
+        __syncthreads();  // the slot is free again; after the last band V is complete
+        if (band == NH - 1) {
+            const int im = blockIdx.x + (u / NH) * gridDim.x;
+            T *dst = small + int64_t(im) * hs * ws;
+            for (int c0 = 0; c0 < hs * ws; c0 += kRingThreads / parts) {
+                const int cell = c0 + tid / parts, part = tid % parts;
+                float sacc = 0.f;
+                int a = 0, j = 0;
+                if (cell < hs * ws) {
+                    a = cell / ws, j = cell % ws;
+                    for (int x = xlo[j] + part; x <= xhi[j]; x += parts) sacc = fmaf(WX[j * W + x], V[a * W + x], sacc);
                 }
+                for (int o = 1; o < parts; o <<= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+                if (cell < hs * ws && part == 0) dst[a * ws + j] = from_f32<T>(sacc);
             }
-            for (int o = 1; o < parts; o <<= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-            if (cell < hs * ws && part == 0) dst[a * ws + j] = from_f32<T>(sacc);
+            __syncthreads();  // V is rewritten by the next image's first band
         }
-        __syncthreads();  // V and slot k&1 are free again
     }
 }
 
@@ -503,14 +531,20 @@ int resample_reduce_launch(const void *big, void *small, int BC, int H, int W, i
     // ring variant: two whole images + tables in shared memory, one CTA per SM walking over its images
     const size_t esz = dtype == MMI_F32 ? 4 : 2;
     const size_t img_b = (size_t(H) * W * esz + 127) & ~size_t(127);
-    int R = W4 > 0 ? kRingThreads / (hs * W4) : 1;
-    R = R < 1 ? 1 : (R > 4 ? 4 : R);
-    auto ring_bytes = [&](int r) {
-        return (size_t(4) * (H + W) + 2 * ws + 2 * hs + 4 + size_t(r) * hs * W + 4 + 32) * sizeof(float) + 2 * img_b;
-    };
-    while (R > 1 && ring_bytes(R) > 227 * 1024) --R;
-    const size_t smem_ring = ring_bytes(R);
-    const bool ring = (W & 3) == 0 && (size_t(H) * W * esz) % 16 == 0 && smem_ring <= 227 * 1024 && img_b >= 32 * 1024 &&
+    // row bands: the fewest per image such that kRingSlots slots fit next to the tables (band bytes a multiple of 16)
+    const size_t ring_fixed = (size_t(4) * (H + W) + 2 * ws + 2 * hs + 4 + size_t(hs) * W + size_t(hs) * H + size_t(ws) * W + 4 +
+                               2 * kRingSlots + 32) * sizeof(float);
+    const size_t slot_budget = ring_fixed < 227 * 1024 ? (227 * 1024 - ring_fixed) / kRingSlots : 0;
+    int NH = 1, RBn = H;
+    while (NH < H && ((size_t(RBn) * W * esz + 127) & ~size_t(127)) > slot_budget) {
+        ++NH;
+        RBn = (H + NH - 1) / NH;
+        if (esz == 2 && (RBn & 1)) ++RBn;  // W % 4 == 0 only guarantees 8-byte rows
+    }
+    const size_t slot_stride = (size_t(RBn) * W * esz + 127) & ~size_t(127);
+    NH = (H + RBn - 1) / RBn;
+    const size_t smem_ring = ring_fixed + kRingSlots * slot_stride;
+    const bool ring = (W & 3) == 0 && (size_t(RBn) * W * esz) % 16 == 0 && slot_stride <= slot_budget && img_b >= 32 * 1024 &&
                       BC >= 2 * sm_count();
 #define MMI_RS_REDUCE(T)                                                                                                \
     do {                                                                                                                \
@@ -518,7 +552,7 @@ int resample_reduce_launch(const void *big, void *small, int BC, int H, int W, i
             auto kern = resample_reduce_ring_kernel<T>;                                                                 \
             if (int e = opt_in_smem(kern, smem_ring)) return e;                                                         \
             kern<<<min(BC, sm_count()), kRingThreads, smem_ring, st>>>(static_cast<const T *>(big), static_cast<T *>(small), BC, \
-                                                                        H, W, hs, ws, mode, R);                         \
+                                                                        H, W, hs, ws, mode, NH, RBn, uint32_t(slot_stride)); \
         } else if (rows) {                                                                                              \
             auto kern = resample_reduce_rows_kernel<T>;                                                                 \
             if (int e = opt_in_smem(kern, smem)) return e;                                                              \
