@@ -330,3 +330,64 @@ def test_resample_fuzz_vs_oracle():
         scale_u = float(up.detach().abs().double().sum()) + 1.0
         assert abs(lhs_p - rhs_p) <= 1e-4 * scale_p, tag
         assert abs(lhs_u - rhs_u) <= 1e-4 * scale_u, tag
+
+
+def test_new_kernels_stay_inside_their_outputs():
+    """no memcheck tool on the GPU pool: every output of the resampling / token-layout / pattern kernels is carved out of a
+    sentinel-filled arena and the guard bands on both sides must survive (ragged shapes: partial tiles, vector + scalar paths)."""
+    from mmidet_b200 import _lib, ops
+    lib = _lib.load()
+    P, DT, ST = ops._ptr, ops._DT, ops._stream
+    GUARD = 4096
+
+    def arena(n, dtype):
+        buf = torch.full((n + 2 * GUARD,), 7.0, device="cuda", dtype=dtype)  # sentinel 7 everywhere
+        return buf, buf[GUARD:GUARD + n]
+
+    def intact(buf, n):
+        return bool((buf[:GUARD] == 7).all()) and bool((buf[GUARD + n:] == 7).all())
+
+    for dt in (torch.float32, torch.bfloat16):
+        for (B, C, H, W, hs, ws) in [(2, 3, 160, 160, 8, 8), (1, 5, 37, 53, 8, 8), (3, 100, 96, 100, 8, 8), (2, 150, 128, 136, 8, 8),
+                                     (1, 7, 20, 24, 4, 6)]:
+            big = torch.randn(B, C, H, W, device="cuda").to(dt)
+            small = torch.randn(B, C, hs, ws, device="cuda").to(dt)
+            for fn, src, n in (("mmi_avgpool_fwd", big, B * C * hs * ws), ("mmi_upsample_bilinear_bwd", big, B * C * hs * ws),
+                               ("mmi_upsample_bilinear_fwd", small, B * C * H * W), ("mmi_avgpool_bwd", small, B * C * H * W)):
+                buf, out = arena(n, dt)
+                _lib.check(getattr(lib, fn)(P(src), P(out), B * C, H, W, hs, ws, DT[dt], ST(src)), fn)
+                torch.cuda.synchronize()
+                assert intact(buf, n), (fn, dt, B, C, H, W)
+                assert bool(torch.isfinite(out.float()).all()) and not bool((out == 7).all())
+        for (B, C, HW) in [(2, 136, 168), (1, 72, 63), (3, 256, 400), (1, 8, 16), (2, 200, 272)]:
+            rgb, ir = torch.randn(B, C, HW, device="cuda").to(dt), torch.randn(B, C, HW, device="cuda").to(dt)
+            n = B * 2 * HW * C
+            buf, tok = arena(n, dt)
+            _lib.check(lib.mmi_tokens_gather(P(rgb), P(ir), P(tok), B, C, HW, DT[dt], ST(rgb)), "mmi_tokens_gather")
+            b1, o1 = arena(B * C * HW, dt)
+            b2, o2 = arena(B * C * HW, dt)
+            _lib.check(lib.mmi_tokens_scatter(P(tok), P(o1), P(o2), B, C, HW, DT[dt], ST(rgb)), "mmi_tokens_scatter")
+            torch.cuda.synchronize()
+            assert intact(buf, n) and intact(b1, B * C * HW) and intact(b2, B * C * HW), (dt, B, C, HW)
+            assert torch.equal(o1.view(B, C, HW), rgb) and torch.equal(o2.view(B, C, HW), ir)
+    # pattern path: tokens, rows, loss and the backward outputs
+    for (B, C, h, w) in [(1, 8, 8, 8), (9, 40, 5, 7), (3, 100, 8, 8)]:
+        Pn = h * w
+        vis, ir = torch.randn(B, C, h, w, device="cuda"), torch.randn(B, C, h, w, device="cuda")
+        w1, w2 = torch.randn(8, C, device="cuda"), torch.randn(C, 8, device="cuda")
+        ws = torch.empty(lib.mmi_ffm_pattern_ws_bytes(B, C, Pn), dtype=torch.uint8, device="cuda")
+        bt, tok = arena(B * 2 * Pn * C, torch.float32)
+        br, rows = arena(18 * B * Pn, torch.float32)
+        bl, loss = arena(1, torch.float32)
+        _lib.check(lib.mmi_ffm_pattern_fwd(P(vis), P(ir), P(w1), P(w2), P(tok), P(rows), P(loss), P(ws), B, C, h, w, DT[torch.float32],
+                                           ST(vis)), "mmi_ffm_pattern_fwd")
+        dtok = torch.randn(B, 2 * Pn, C, device="cuda")
+        bv, dvis = arena(B * C * Pn, torch.float32)
+        bi, dir_ = arena(B * C * Pn, torch.float32)
+        b1, dw1 = arena(8 * C, torch.float32)
+        b2, dw2 = arena(8 * C, torch.float32)
+        _lib.check(lib.mmi_ffm_pattern_bwd(P(vis), P(ir), P(dtok), P(rows), P(w1), P(w2), P(dvis), P(dir_), P(dw1), P(dw2), P(ws), B, C, Pn,
+                                           DT[torch.float32], ST(vis)), "mmi_ffm_pattern_bwd")
+        torch.cuda.synchronize()
+        for buf, n in ((bt, B * 2 * Pn * C), (br, 18 * B * Pn), (bl, 1), (bv, B * C * Pn), (bi, B * C * Pn), (b1, 8 * C), (b2, 8 * C)):
+            assert intact(buf, n), (B, C, h, w, n)
