@@ -340,3 +340,47 @@ def test_fuzz_against_oracle(seed):
         if leaves[k].grad is not None:
             res[n] = leaves[k].grad.cpu().numpy()
     _compare(res, ref, TOL32)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 77, 72), (1, 130, 8), (3, 200, 136), (1, 1000, 64), (2, 64, 64)])
+def test_scan_kernels_stay_inside_their_outputs(shape, dtype):
+    """every output and workspace of the forward / backward scan carved out of a sentinel arena: the guard bands on both
+    sides must survive (ragged L and ED, L split over several CTAs at batch 1) -- stands in for a memcheck tool."""
+    from mmidet_b200 import _lib, ops
+    lib = _lib.load()
+    P, DT, ST = ops._ptr, ops._DT, ops._stream
+    B, L, ED = shape
+    N, GUARD = 16, 4096
+    arenas = []
+
+    def carve(n, dt):
+        buf = torch.full((n + 2 * GUARD,), 7.0 if dt != torch.uint8 else 7, device="cuda", dtype=dt)
+        arenas.append((buf, n))
+        return buf[GUARD:GUARD + n]
+
+    torch.manual_seed(L)
+    x, z, dout = (torch.randn(B, L, ED, device="cuda").to(dtype) for _ in range(3))
+    delta = torch.nn.functional.softplus(torch.randn(B, L, ED, device="cuda") - 3).to(dtype)
+    Bm, Cm = torch.randn(B, L, N, device="cuda").to(dtype), torch.randn(B, L, N, device="cuda").to(dtype)
+    A = -torch.arange(1, N + 1, device="cuda", dtype=torch.float32).repeat(ED, 1).contiguous()
+    D = torch.ones(ED, device="cuda")
+    chunk = lib.mmi_selscan_chunk()
+    nchk = (L + chunk - 1) // chunk
+    out = carve(B * L * ED, dtype)
+    hT = carve(B * ED * N, torch.float32)
+    chk = carve(B * nchk * ED * N, torch.float32)
+    wsf = carve(max(int(lib.mmi_selscan_fwd_ws_bytes(B, L, ED, N)), 16), torch.uint8)
+    _lib.check(lib.mmi_selscan_fwd(P(x), P(delta), P(z), P(A), P(Bm), P(Cm), P(D), None, P(out), P(hT), P(chk), P(wsf), B, L, ED, N,
+                                   ED, ED, ED, ED, chunk, DT[dtype], 0, ST(x)), "mmi_selscan_fwd")
+    dx, dd, dz = carve(B * L * ED, dtype), carve(B * L * ED, dtype), carve(B * L * ED, dtype)
+    dA, dD = carve(ED * N, torch.float32), carve(ED, torch.float32)
+    dB, dC = carve(B * L * N, dtype), carve(B * L * N, dtype)
+    wsb = carve(max(int(lib.mmi_selscan_bwd_ws_bytes(B, L, ED, N)), 16), torch.uint8)
+    _lib.check(lib.mmi_selscan_bwd(P(x), P(delta), P(z), P(A), P(Bm), P(Cm), P(D), P(dout), P(chk), P(dx), P(dd), P(dz), P(dA), P(dB),
+                                   P(dC), P(dD), P(wsb), B, L, ED, N, ED, ED, ED, ED, chunk, DT[dtype], 0, ST(x)), "mmi_selscan_bwd")
+    torch.cuda.synchronize()
+    for i, (buf, n) in enumerate(arenas):
+        assert bool((buf[:GUARD] == 7).all()) and bool((buf[GUARD + n:] == 7).all()), f"guard band of arena {i} overwritten"
+    for t in (out, dx, dd, dz, dA, dD, dB, dC):
+        assert bool(torch.isfinite(t.float()).all())
