@@ -208,3 +208,38 @@ def test_graphed_fusion_matches_eager():
         c, d = fast(x)
         assert torch.allclose(a, c, atol=1e-6, rtol=1e-5) and torch.allclose(b, d, atol=1e-6, rtol=1e-5)
     assert len(fast._graphs) == 2
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_conv_and_rmsnorm_stay_inside_their_outputs(dtype):
+    """outputs of the conv prologue and RMSNorm kernels carved out of sentinel arenas (ragged L, ED / C that do not fill a
+    128-channel group, rows that do not fill a warp strip): guard bands must survive -- stands in for a memcheck tool."""
+    from mmidet_b200 import _lib, ops
+    lib = _lib.load()
+    P, DT, ST = ops._ptr, ops._DT, ops._stream
+    GUARD = 4096
+    arenas = []
+
+    def carve(n, dt):
+        buf = torch.full((n + 2 * GUARD,), 7.0, device="cuda", dtype=dt)
+        arenas.append((buf, n))
+        return buf[GUARD:GUARD + n]
+
+    for (B, L, ED) in [(2, 77, 72), (1, 130, 8), (3, 33, 136), (1, 257, 512)]:
+        x, gy = torch.randn(B, L, ED, device="cuda").to(dtype), torch.randn(B, L, ED, device="cuda").to(dtype)
+        w, b = torch.randn(ED, 4, device="cuda"), torch.randn(ED, device="cuda")
+        y, dx = carve(B * L * ED, dtype), carve(B * L * ED, dtype)
+        dw, db = carve(ED * 4, torch.float32), carve(ED, torch.float32)
+        _lib.check(lib.mmi_causal_conv1d_fwd(P(x), P(w), P(b), P(y), B, L, ED, 4, ED, ED, DT[dtype], 1, ST(x)), "conv fwd")
+        _lib.check(lib.mmi_causal_conv1d_bwd(P(x), P(w), P(b), P(gy), P(dx), P(dw), P(db), B, L, ED, 4, ED, ED, ED, DT[dtype], 1, ST(x)),
+                   "conv bwd")
+    for (rows, C) in [(77, 72), (1, 8), (4097, 256), (130, 1024)]:
+        x, g = torch.randn(rows, C, device="cuda").to(dtype), torch.randn(rows, C, device="cuda").to(dtype)
+        w = torch.rand(C, device="cuda") + 0.5
+        y, dx, dw = carve(rows * C, dtype), carve(rows * C, dtype), carve(C, torch.float32)
+        _lib.check(lib.mmi_rmsnorm_fwd(P(x), P(w), P(y), rows, C, C, C, 1e-5, DT[dtype], -1, ST(x)), "rmsnorm fwd")
+        _lib.check(lib.mmi_rmsnorm_bwd(P(x), P(w), P(g), P(dx), P(dw), rows, C, C, C, C, 1e-5, DT[dtype], -1, ST(x)), "rmsnorm bwd")
+    torch.cuda.synchronize()
+    for i, (buf, n) in enumerate(arenas):
+        assert bool((buf[:GUARD] == 7).all()) and bool((buf[GUARD + n:] == 7).all()), f"guard band of arena {i} overwritten"
+        assert bool(torch.isfinite(buf[GUARD:GUARD + n].float()).all())
