@@ -94,6 +94,10 @@ int64_t mmi_pscan_ws_bytes(int B, int L, int D, int N);
 int mmi_pscan_fwd(const float *A, const float *X, float *H, void *ws, int B, int L, int D, int N, void *stream);
 int mmi_pscan_bwd(const float *A, const float *H, const float *gH, float *gA, float *gX, void *ws, int B, int L, int D,
                   int N, void *stream);
+/* fp64 variants of the two above (models/pscan.py is dtype-generic; fp64 is what its own gradcheck-style use needs) */
+int mmi_pscan_fwd_f64(const double *A, const double *X, double *H, void *ws, int B, int L, int D, int N, void *stream);
+int mmi_pscan_bwd_f64(const double *A, const double *H, const double *gH, double *gA, double *gX, void *ws, int B, int L,
+                      int D, int N, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Fusion Focus Module Fourier step.  Replaces extract_frequency2 (models/common.py:37-69):

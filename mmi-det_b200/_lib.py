@@ -88,6 +88,8 @@ _SIGNATURES = {
     "mmi_pscan_ws_bytes": (_i64, [_i] * 4),
     "mmi_pscan_fwd": (_i, [_vp] * 4 + [_i] * 4 + [_vp]),
     "mmi_pscan_bwd": (_i, [_vp] * 6 + [_i] * 4 + [_vp]),
+    "mmi_pscan_fwd_f64": (_i, [_vp] * 4 + [_i] * 4 + [_vp]),
+    "mmi_pscan_bwd_f64": (_i, [_vp] * 6 + [_i] * 4 + [_vp]),
     "mmi_ffm_kept_range": (None, [_i, _i] + [_c.POINTER(_i)] * 4),
     "mmi_ffm_extract": (_i, [_vp] * 4 + [_i] * 4 + [_vp]),
     "mmi_separation_loss": (_i, [_vp] * 2 + [_i] * 2 + [_vp]),
@@ -119,11 +121,15 @@ def load() -> ctypes.CDLL:
     if _lib is not None:
         return _lib
     if needs_build():
+        # a source newer than the library must compile: never run yesterday's binary against today's sources.  The one
+        # exception is a box without nvcc (the library was built elsewhere and shipped): then the shipped file is loaded.
         try:
             build()
-        except (FileNotFoundError, RuntimeError) as e:
+        except FileNotFoundError as e:
             if not os.path.exists(SO_PATH):
-                raise RuntimeError(f"libmmidet_b200.so is not built and cannot be built here: {e}") from e
+                raise RuntimeError(f"libmmidet_b200.so is not built and nvcc is not available here: {e}") from e
+        except RuntimeError as e:
+            raise RuntimeError(f"libmmidet_b200.so is older than its sources and the rebuild failed: {e}") from e
     lib = ctypes.CDLL(SO_PATH)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError => header/library mismatch, fail loudly

@@ -80,6 +80,9 @@ static int check_scan_args(const char *who, int B, int L, int ED, int N, int dty
 int pscan_fwd_launch(const float *A, const float *X, float *H, float *ws, int B, int L, int DN, cudaStream_t st);
 int pscan_bwd_launch(const float *A, const float *H, const float *gH, float *gA, float *gX, float *ws, int B, int L, int DN,
                      cudaStream_t st);
+int pscan_fwd_launch_f64(const double *A, const double *X, double *H, double *ws, int B, int L, int DN, cudaStream_t st);
+int pscan_bwd_launch_f64(const double *A, const double *H, const double *gH, double *gA, double *gX, double *ws, int B, int L,
+                         int DN, cudaStream_t st);
 int64_t pscan_ws_bytes(int B, int L, int D, int N);
 int ffm_extract_launch(const void *img, void *low, void *high, float *high_mul, int BC, int H, int W, int dtype,
                        cudaStream_t st);
@@ -197,6 +200,19 @@ int mmi_pscan_bwd(const float *A, const float *H, const float *gH, float *gA, fl
     if (!A || !H || !gH || !gA || !gX || !ws) { set_error("mmi_pscan_bwd: null pointer"); return MMI_ERR_ARG; }
     if (int e = check_pscan("mmi_pscan_bwd", B, L, D, N)) return e;
     return pscan_bwd_launch(A, H, gH, gA, gX, static_cast<float *>(ws), B, L, D * N, static_cast<cudaStream_t>(stream));
+}
+
+int mmi_pscan_fwd_f64(const double *A, const double *X, double *H, void *ws, int B, int L, int D, int N, void *stream) {
+    if (!A || !X || !H || !ws) { set_error("mmi_pscan_fwd_f64: null pointer"); return MMI_ERR_ARG; }
+    if (int e = check_pscan("mmi_pscan_fwd_f64", B, L, D, N)) return e;
+    return pscan_fwd_launch_f64(A, X, H, static_cast<double *>(ws), B, L, D * N, static_cast<cudaStream_t>(stream));
+}
+
+int mmi_pscan_bwd_f64(const double *A, const double *H, const double *gH, double *gA, double *gX, void *ws, int B, int L, int D,
+                      int N, void *stream) {
+    if (!A || !H || !gH || !gA || !gX || !ws) { set_error("mmi_pscan_bwd_f64: null pointer"); return MMI_ERR_ARG; }
+    if (int e = check_pscan("mmi_pscan_bwd_f64", B, L, D, N)) return e;
+    return pscan_bwd_launch_f64(A, H, gH, gA, gX, static_cast<double *>(ws), B, L, D * N, static_cast<cudaStream_t>(stream));
 }
 
 int mmi_ffm_extract(const void *img, void *low, void *high, float *high_mul, int BC, int H, int W, int dtype,

@@ -87,6 +87,99 @@ __global__ void __launch_bounds__(128) ffm_extract_kernel(const T *__restrict__ 
     }
 }
 
+// Maps larger than 64 x 64 (the reference only ever calls extract_frequency2 on the 8 x 8 pooled maps, but the helper is
+// public and size-generic): the kept block is nr x nc = about (W/8) x (W/8) bins of the shifted spectrum, so the
+// projection is evaluated through those bins only --
+//     T1[h,j] = sum_w x[h,w] e^{-i kc_j w},  X[i,j] = sum_h T1[h,j] e^{-i kr_i h},
+//     U[h,j]  = sum_i X[i,j] e^{+i kr_i h},  low[h,w] = Re sum_j U[h,j] e^{+i kc_j w} / (H W)
+// one CTA per (b, c) image, T1 / U / X and the two twiddle tables in shared memory, x read from global memory twice.
+constexpr int kFfmWideThreads = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kFfmWideThreads) ffm_extract_wide_kernel(const T *__restrict__ img, __half *__restrict__ low,
+                                                                           __half *__restrict__ high, float *__restrict__ high_mul,
+                                                                           int H, int W, int r0, int r1, int c0, int c1) {
+    extern __shared__ float sm[];
+    const int nr = r1 - r0, nc = c1 - c0;
+    float2 *twH = reinterpret_cast<float2 *>(sm);  // [H] (cos, sin)(2 pi k / H)
+    float2 *twW = twH + H;                         // [W]
+    float2 *T1 = twW + W;                          // [H][nc]
+    float2 *U = T1 + size_t(H) * nc;               // [H][nc]
+    float2 *X = U + size_t(H) * nc;                // [nr][nc]
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const T *x = img + int64_t(blockIdx.x) * H * W;
+    const int64_t off = int64_t(blockIdx.x) * H * W;
+    for (int i = tid; i < H + W; i += nt) {
+        const bool row = i < H;
+        const int n = row ? H : W, k = row ? i : i - H;
+        float sn, cs;
+        sincospif(2.0f * float(k) / float(n), &sn, &cs);
+        (row ? twH : twW)[k] = make_float2(cs, sn);
+    }
+    __syncthreads();
+    auto freq = [](int s, int n) {  // fftshift index -> frequency
+        int k = (s - n / 2) % n;
+        return k < 0 ? k + n : k;
+    };
+    for (int it = tid; it < H * nc; it += nt) {
+        const int h = it / nc, j = it % nc, kc = freq(c0 + j, W);
+        float re = 0.f, im = 0.f;
+        int idx = 0;
+        for (int w = 0; w < W; ++w) {
+            const float v = to_f32<T>(x[h * W + w]);
+            const float2 t = twW[idx];
+            re = fmaf(v, t.x, re);
+            im = fmaf(-v, t.y, im);
+            idx += kc;
+            if (idx >= W) idx -= W;
+        }
+        T1[it] = make_float2(re, im);
+    }
+    __syncthreads();
+    for (int it = tid; it < nr * nc; it += nt) {
+        const int i = it / nc, j = it % nc, kr = freq(r0 + i, H);
+        float re = 0.f, im = 0.f;
+        int idx = 0;
+        for (int h = 0; h < H; ++h) {
+            const float2 a = T1[h * nc + j], t = twH[idx];  // a * conj(t)
+            re += a.x * t.x + a.y * t.y;
+            im += a.y * t.x - a.x * t.y;
+            idx += kr;
+            if (idx >= H) idx -= H;
+        }
+        X[it] = make_float2(re, im);
+    }
+    __syncthreads();
+    for (int it = tid; it < H * nc; it += nt) {
+        const int h = it / nc, j = it % nc;
+        float re = 0.f, im = 0.f;
+        for (int i = 0; i < nr; ++i) {
+            const int kr = freq(r0 + i, H);
+            const float2 a = X[i * nc + j], t = twH[int((int64_t(kr) * h) % H)];  // a * t
+            re += a.x * t.x - a.y * t.y;
+            im += a.x * t.y + a.y * t.x;
+        }
+        U[it] = make_float2(re, im);
+    }
+    __syncthreads();
+    const float scale = 1.0f / (float(H) * float(W));
+    for (int it = tid; it < H * W; it += nt) {
+        const int h = it / W, w = it % W;
+        float lo = 0.f;
+        for (int j = 0; j < nc; ++j) {
+            const int kc = freq(c0 + j, W);
+            const float2 a = U[h * nc + j], t = twW[int((int64_t(kc) * w) % W)];
+            lo += a.x * t.x - a.y * t.y;
+        }
+        lo *= scale;
+        const float xv = to_f32<T>(x[it]);
+        const __half l16 = __float2half_rn(lo), h16 = __float2half_rn(xv - lo);
+        if (low) low[off + it] = l16;
+        if (high) high[off + it] = h16;
+        if (high_mul) high_mul[off + it] = __half2float(h16) * xv;
+    }
+}
+
 // models/common.py:128-139 in closed form; one CTA.
 __global__ void __launch_bounds__(256) separation_loss_kernel(const float *__restrict__ M, float *__restrict__ loss, int l,
                                                               int K) {
@@ -152,14 +245,39 @@ void ffm_kept_range(int H, int W, int *r0, int *r1, int *c0, int *c1) {
 
 int ffm_extract_launch(const void *img, void *low, void *high, float *high_mul, int BC, int H, int W, int dtype,
                        cudaStream_t st) {
-    if (H > kFfmMax || W > kFfmMax || H < 1 || W < 1) {
-        set_error("mmi_ffm_extract: H, W must be in [1, %d] (got %dx%d)", kFfmMax, H, W);
-        return MMI_ERR_UNSUPPORTED;
+    if (H < 1 || W < 1) {
+        set_error("mmi_ffm_extract: bad map size %dx%d", H, W);
+        return MMI_ERR_ARG;
     }
     int r0, r1, c0, c1;
     ffm_kept_range(H, W, &r0, &r1, &c0, &c1);
-    const size_t smem = (size_t(3) * H * W + 2 * (H + W)) * sizeof(float);
     __half *lo = static_cast<__half *>(low), *hi = static_cast<__half *>(high);
+    if (H > kFfmMax || W > kFfmMax) {  // large maps: projection through the kept bins only
+        const size_t nr = size_t(r1 - r0), nc = size_t(c1 - c0);
+        const size_t smem_w = (size_t(H) + W + 2 * size_t(H) * nc + nr * nc) * sizeof(float2);
+        if (smem_w > 200 * 1024) {
+            set_error("mmi_ffm_extract: %dx%d map keeps %zux%zu bins, which needs %zu bytes of shared memory (limit 200 KiB)", H, W,
+                      nr, nc, smem_w);
+            return MMI_ERR_UNSUPPORTED;
+        }
+#define MMI_FFM_WIDE(T)                                                                                                  \
+    do {                                                                                                                 \
+        auto kern = ffm_extract_wide_kernel<T>;                                                                          \
+        if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_w)),     \
+                               "ffm smem attribute"))                                                                    \
+            return e;                                                                                                    \
+        kern<<<BC, kFfmWideThreads, smem_w, st>>>(static_cast<const T *>(img), lo, hi, high_mul, H, W, r0, r1, c0, c1);  \
+    } while (0)
+        switch (dtype) {
+            case MMI_F32: MMI_FFM_WIDE(float); break;
+            case MMI_BF16: MMI_FFM_WIDE(__nv_bfloat16); break;
+            case MMI_F16: MMI_FFM_WIDE(__half); break;
+            default: set_error("mmi_ffm_extract: unknown dtype %d", dtype); return MMI_ERR_ARG;
+        }
+#undef MMI_FFM_WIDE
+        return check_cuda(cudaGetLastError(), "ffm_extract (wide) launch");
+    }
+    const size_t smem = (size_t(3) * H * W + 2 * (H + W)) * sizeof(float);
 #define MMI_FFM_LAUNCH(T)                                                                                               \
     do {                                                                                                                \
         auto kern = ffm_extract_kernel<T>;                                                                              \

@@ -10,7 +10,7 @@
 
 namespace mmi {
 
-constexpr int kRmsMaxC = 1024;           // channels per row held in registers (32 lanes x 4 x 8 float4 groups)
+// rows up to 1024 channels: one warp per row, the row in registers (32 lanes x 4 x 8 float4 groups); wider rows: one CTA per row
 constexpr int kRmsRowsPerWarp = 32;       // rows per warp strip in the backward (dw is reduced over the strip, then over the
                                           // block's four warps in shared memory: the C addresses of dw sit in a handful of L2
                                           // slices, so every atomic saved matters)
@@ -201,6 +201,114 @@ __global__ void __launch_bounds__(128) rmsnorm_bwd_kernel(const T *__restrict__ 
     }
 }
 
+// ---- wide rows (1024 < C <= 4096, e.g. d_model = 1280 at P5 of YOLOv5x): one 256-thread CTA per row strip -------------
+constexpr int kRmsWideThreads = 256;
+constexpr int kRmsWideMaxC = 4096;
+constexpr int kRmsWideRows = 8;  // rows per CTA strip in the backward
+
+__device__ __forceinline__ float block_sum256(float v, float *red) {  // red: 8 floats; every thread gets the total
+    v = warp_sum(v);
+    __syncthreads();  // protects `red` against the previous call's readers
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < kRmsWideThreads / 32; ++i) t += red[i];
+    return t;
+}
+
+template <typename T, typename TY, int NV>
+__global__ void __launch_bounds__(kRmsWideThreads) rmsnorm_wide_fwd_kernel(const T *__restrict__ x, const float *__restrict__ w,
+                                                                           TY *__restrict__ y, int64_t rows, int C, int64_t x_ld,
+                                                                           int64_t y_ld, float eps) {
+    __shared__ float red[8];
+    const int64_t row = blockIdx.x;
+    float v[NV][4];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * kRmsWideThreads + threadIdx.x) * 4;
+        if (c < C) {
+            rms_load4<T>(x + row * x_ld + c, v[i]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ss = fmaf(v[i][k], v[i][k], ss);
+        }
+    }
+    const float r = rsqrtf(block_sum256(ss, red) / float(C) + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * kRmsWideThreads + threadIdx.x) * 4;
+        if (c < C) {
+            const float4 ww = __ldg(reinterpret_cast<const float4 *>(w + c));
+            float o[4] = {v[i][0] * r * ww.x, v[i][1] * r * ww.y, v[i][2] * r * ww.z, v[i][3] * r * ww.w};
+            rms_store4<TY>(y + row * y_ld + c, o);
+        }
+    }
+}
+
+template <typename T, typename TY, int NV>
+__global__ void __launch_bounds__(kRmsWideThreads) rmsnorm_wide_bwd_kernel(const T *__restrict__ x, const float *__restrict__ w,
+                                                                           const TY *__restrict__ dy, T *__restrict__ dx,
+                                                                           float *__restrict__ dw, int64_t rows, int C, int64_t x_ld,
+                                                                           int64_t dy_ld, int64_t dx_ld, float eps) {
+    __shared__ float red[8];
+    const int64_t row0 = int64_t(blockIdx.x) * kRmsWideRows;
+    const int nrow = int(min(int64_t(kRmsWideRows), rows - row0));
+    float wv[NV][4], dwa[NV][4];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * kRmsWideThreads + threadIdx.x) * 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dwa[i][k] = 0.f, wv[i][k] = 0.f;
+        if (c < C) {
+            const float4 ww = __ldg(reinterpret_cast<const float4 *>(w + c));
+            wv[i][0] = ww.x; wv[i][1] = ww.y; wv[i][2] = ww.z; wv[i][3] = ww.w;
+        }
+    }
+    for (int rr = 0; rr < nrow; ++rr) {
+        const int64_t row = row0 + rr;
+        float xv[NV][4], gv[NV][4];
+        float ss = 0.f, sg = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * kRmsWideThreads + threadIdx.x) * 4;
+            if (c < C) {
+                rms_load4<T>(x + row * x_ld + c, xv[i]);
+                rms_load4<TY>(dy + row * dy_ld + c, gv[i]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    ss = fmaf(xv[i][k], xv[i][k], ss);
+                    sg = fmaf(gv[i][k] * wv[i][k], xv[i][k], sg);
+                }
+            }
+        }
+        ss = block_sum256(ss, red);
+        sg = block_sum256(sg, red);
+        const float r = rsqrtf(ss / float(C) + eps);
+        const float coef = r * r * r * sg / float(C);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * kRmsWideThreads + threadIdx.x) * 4;
+            if (c < C) {
+                float o[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    o[k] = fmaf(gv[i][k] * wv[i][k], r, -xv[i][k] * coef);
+                    dwa[i][k] = fmaf(gv[i][k] * r, xv[i][k], dwa[i][k]);
+                }
+                rms_store4<T>(dx + row * dx_ld + c, o);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * kRmsWideThreads + threadIdx.x) * 4;
+        if (c < C)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) atomicAdd(dw + c + k, dwa[i][k]);
+    }
+}
+
 // T: dtype of x / dx; TY: dtype of y (forward) and dy (backward) -- equal to T, or 16-bit with fp32 x (autocast: the
 // norm runs in fp32 and its output is consumed by a 16-bit GEMM, so the rounding happens in the kernel's store)
 template <typename T, typename TY> static int rms_launch_t(bool bwd, const void *x, const float *w, const void *dy, void *out, float *dw,
@@ -224,7 +332,20 @@ template <typename T, typename TY> static int rms_launch_t(bool bwd, const void 
     MMI_RMS(4)
     MMI_RMS(8)
 #undef MMI_RMS
-    set_error("rmsnorm: C=%d exceeds %d", C, kRmsMaxC);
+#define MMI_RMS_WIDE(NVV)                                                                                              \
+    if (C <= kRmsWideThreads * 4 * NVV) {                                                                              \
+        if (bwd)                                                                                                       \
+            rmsnorm_wide_bwd_kernel<T, TY, NVV><<<unsigned((rows + kRmsWideRows - 1) / kRmsWideRows), kRmsWideThreads, 0, st>>>( \
+                xp, w, static_cast<const TY *>(dy), static_cast<T *>(out), dw, rows, C, x_ld, dy_ld, out_ld, eps);     \
+        else                                                                                                           \
+            rmsnorm_wide_fwd_kernel<T, TY, NVV><<<unsigned(rows), kRmsWideThreads, 0, st>>>(xp, w, static_cast<TY *>(out), rows, C, \
+                                                                                            x_ld, out_ld, eps);       \
+        return check_cuda(cudaGetLastError(), "rmsnorm (wide rows) launch");                                           \
+    }
+    MMI_RMS_WIDE(2)
+    MMI_RMS_WIDE(4)
+#undef MMI_RMS_WIDE
+    set_error("rmsnorm: C=%d exceeds %d", C, kRmsWideMaxC);
     return MMI_ERR_UNSUPPORTED;
 }
 

@@ -299,7 +299,8 @@ __device__ __forceinline__ void bwd_body(const BwdParams &p, const BwdMaps &tm, 
 #pragma unroll                              // once, in place (sweep A, P1 and P3 all read the activated value)
             for (int u = 0; u < TC; ++u) {
                 const float2 r = ld_pair<T>(sd + u * CH);
-                st_pair<T>(sd + u * CH, make_float2(softplus_fast(r.x), softplus_fast(r.y)));
+                const bool in = t0 + tb + u < L;  // rows past L stay 0 (TMA zero fill), as in the forward kernel
+                st_pair<T>(sd + u * CH, make_float2(in ? softplus_fast(r.x) : 0.f, in ? softplus_fast(r.y) : 0.f));
             }
         }
         // ---- A: dy, dz factor, reverse-scan summary of the chunk ------------------------------------------------

@@ -194,7 +194,8 @@ __device__ __forceinline__ void fwd_body(const FwdParams &p, const FwdMaps &tm, 
 
         if (p.flags & MMI_FLAG_DELTA_SOFTPLUS) {  // fused softplus(dt_proj(.)), models/mamba.py:203: activate this chunk's delta
 #pragma unroll                              // once, in place, rounded to the I/O type exactly as the unfused path does
-            for (int u = 0; u < TC; ++u) sd[u * CH] = from_f32<T>(softplus_fast(to_f32<T>(sd[u * CH])));
+            for (int u = 0; u < TC; ++u)  // rows past L stay 0 (TMA zero fill): identity steps, so hT is h[L-1]
+                sd[u * CH] = from_f32<T>(t0 + tb + u < L ? softplus_fast(to_f32<T>(sd[u * CH])) : 0.f);
         }
         // ---- sweep A: chunk summary by direct evaluation (walk t backwards, S = sum of delta after t) ----------
         float2 acc[8];

@@ -29,6 +29,11 @@ def extract_frequency2(image: torch.Tensor, with_product: bool = False):
     """-> (low, high) float16; with_product=True also returns high * image in fp32 (models/common.py:440-441)."""
     if not image.is_cuda:
         raise RuntimeError("mmidet_b200.extract_frequency2: CUDA tensor required (no CPU path)")
+    if image.requires_grad and torch.is_grad_enabled():
+        # the reference's torch.fft version is differentiable; this kernel is a value-only drop-in (the detector detaches
+        # everything downstream of it, models/yolo_test.py:226-230): refuse rather than return a silent zero gradient
+        raise RuntimeError("mmidet_b200.extract_frequency2 is not differentiable: call it under torch.no_grad() or on a "
+                           "detached tensor (GPT1_fourier.forward goes through ffm.pattern_tokens, which is)")
     lib = _lib.load()
     Bsz, C, H, W = image.shape
     if image.dtype not in _ops._DT:
@@ -49,10 +54,27 @@ def fourier_transform(image: torch.Tensor) -> torch.Tensor:
     return torch.fft.fftshift(torch.fft.fftn(image, dim=(-2, -1)), dim=(-2, -1))
 
 
+def extract_frequency(image: torch.Tensor, threshold: int = 30):
+    """models/common.py:72-93 (no caller in the reference): zero the central 2*threshold block of the shifted spectrum
+    ("low"), the rest is "high"; both returned as the REAL part in fp16, which is what `.half()` of a complex tensor yields.
+    The FFT is the library call (cuFFT through torch.fft), the split is two masked writes."""
+    if not image.is_cuda:
+        raise RuntimeError("mmidet_b200.extract_frequency: CUDA tensor required (no CPU path)")
+    fs = fourier_transform(image.float()).real
+    H, W = image.shape[-2:]
+    ch, cw = H // 2, W // 2
+    low = fs.clone()
+    low[:, :, ch - threshold:ch + threshold, cw - threshold:cw + threshold] = 0  # Python slice semantics, as the reference
+    return low.half(), (fs - low).half()
+
+
 def separation_loss(M: torch.Tensor) -> torch.Tensor:
     """models/common.py:128-139 for M (l, K): sum_{i<j} M_i . M_j / (l (l - 1)), as a 0-d fp32 tensor."""
     if not M.is_cuda:
         raise RuntimeError("mmidet_b200.separation_loss: CUDA tensor required (no CPU path)")
+    if M.requires_grad and torch.is_grad_enabled():
+        raise RuntimeError("mmidet_b200.separation_loss returns a value only (the detector detaches it, "
+                           "models/yolo_test.py:230): call it under torch.no_grad() or on a detached tensor")
     lib = _lib.load()
     Mc = M.detach().float().contiguous()
     out = torch.empty(1, dtype=torch.float32, device=M.device)

@@ -60,9 +60,9 @@ class RMSNorm(nn.Module):
         self.weight = nn.Parameter(torch.ones(d_model))
 
     def forward(self, x):
-        if x.is_cuda and x.shape[-1] % 8 == 0 and x.shape[-1] <= 1024:
-            return ops.rmsnorm(x, self.weight, self.eps)  # one kernel per direction instead of five elementwise passes
-        return x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + self.eps) * self.weight  # odd widths: plain torch
+        # one kernel per direction instead of five elementwise passes; widths up to 4096 in multiples of 8 (every d_model
+        # of the detector family).  No eager fallback: other widths / CPU tensors raise in the operator.
+        return ops.rmsnorm(x, self.weight, self.eps)
 
 
 class MambaBlock(nn.Module):
@@ -119,37 +119,40 @@ class MambaBlock(nn.Module):
         L = x.shape[1]
         xz = self.in_proj(x)
         xs, z = xz.chunk(2, dim=-1)  # views of one GEMM output: passed to the kernel by row pitch, never copied
-        if self.config.d_conv <= 4 and self.conv1d.groups == self.conv1d.in_channels:
-            # depthwise causal conv + SiLU on the channels-last tokens (no transposes, models/mamba.py:176-180)
-            xs = ops.causal_conv1d_silu(xs, self.conv1d.weight, self.conv1d.bias)
-        else:  # kernel sizes the fused kernel does not cover: stock cuDNN path
-            xs = F.silu(self.conv1d(xs.transpose(1, 2))[:, :, :L].transpose(1, 2))
+        if self.config.d_conv > 4 or self.conv1d.groups != self.conv1d.in_channels:
+            raise RuntimeError(f"mmidet_b200.MambaBlock: d_conv={self.config.d_conv} is outside the fused causal conv kernel "
+                               "(depthwise, kernel size <= 4; the reference default is 4) -- there is no eager fallback")
+        # depthwise causal conv + SiLU on the channels-last tokens (no transposes, models/mamba.py:176-180)
+        xs = ops.causal_conv1d_silu(xs, self.conv1d.weight, self.conv1d.bias)
         y = self.ssm(xs, z=z)  # = ssm(x) * silu(z): the gate of models/mamba.py:184-186 is fused into the scan
         return self.out_proj(y.to(xz.dtype))
 
-    # -- single-token recurrent inference (models/mamba.py:289-353); unused by the detector, kept as plain torch ----
+    # -- single-token recurrent inference (models/mamba.py:289-353): same cache contract (h (B, ED, N) or None, inputs
+    #    (B, ED, d_conv-1)); the conv window and the one-step scan run on the same kernels as forward() (L = d_conv / L = 1,
+    #    state passed through h0 -> hT), the projections on cuBLAS
     def step(self, x, cache):
         h, inputs = cache
         xz = self.in_proj(x)
         xs, z = xz.chunk(2, dim=1)
         xc = xs.unsqueeze(2)
-        xs = F.silu(self.conv1d(torch.cat([inputs, xc], dim=2))[:, :, self.config.d_conv - 1])
-        y, h = self.ssm_step(xs, h)
-        out = self.out_proj(y * F.silu(z))
-        return out, (h, torch.cat([inputs[:, :, 1:], xc], dim=2))
+        win = torch.cat([inputs.to(xs.dtype), xc], dim=2).transpose(1, 2).contiguous()  # (B, d_conv, ED): the causal window
+        xs = ops.causal_conv1d_silu(win, self.conv1d.weight, self.conv1d.bias)[:, -1]
+        y, h = self.ssm_step(xs, h, z=z)
+        out = self.out_proj(y.to(xz.dtype))
+        return out, (h, torch.cat([inputs[:, :, 1:], xc.to(inputs.dtype)], dim=2))
 
-    def ssm_step(self, x, h):
+    def ssm_step(self, x, h, z=None):
+        """models/mamba.py:322-353: one step of the recurrence from state `h` (None = zeros); returns (y, h_new).
+        `z` (B, ED) additionally fuses the gate y * silu(z) of step() (models/mamba.py:311-313)."""
         c = self.config
         A = -torch.exp(self.A_log.float())
         delta, B, C = torch.split(self.x_proj(x), [c.dt_rank, c.d_state, c.d_state], dim=-1)
-        delta = F.softplus(self.dt_proj(delta))
-        dA = torch.exp(delta.unsqueeze(-1) * A)
-        dBx = delta.unsqueeze(-1) * B.unsqueeze(1) * x.unsqueeze(-1)
-        if h is None:
-            h = torch.zeros(x.size(0), c.d_inner, c.d_state, device=dA.device, dtype=dA.dtype)
-        h = dA * h + dBx
-        y = (h @ C.unsqueeze(-1)).squeeze(2) + self.D.float() * x
-        return y, h
+        delta_pre = self.dt_proj(delta)
+        one = lambda t: t.unsqueeze(1).contiguous()
+        y, hT, _, _ = ops.selscan_fwd_raw(one(x), one(delta_pre), A, one(B), one(C), self.D.float(),
+                                          z=None if z is None else one(z), h0=h, want_state=True,
+                                          flags=ops._lib.FLAG_DELTA_SOFTPLUS)
+        return y[:, 0], hT
 
 
 class ResidualBlock(nn.Module):
@@ -198,21 +201,26 @@ class MambaFusion(nn.Module):
         super().__init__()
         cfg = (config_cls or MambaConfig)(d_model=d_model, n_layers=n_layer)
         self.n_embd = d_model
+        self.reference_glue = block_cls is not None
         self.layers = nn.ModuleList([(block_cls or ResidualBlock)(cfg) for _ in range(n_layer)])
 
     def forward(self, x):
         rgb, ir = x[0], x[1]
         B, C, H, W = rgb.shape
-        if rgb.is_cuda and rgb.dtype in ops._DT and rgb.dtype == ir.dtype:
-            tok = ops.tokens_gather(rgb, ir)  # (B, 2HW, C), VIS tokens then IR tokens: one tiled transpose
+        if self.reference_glue:
+            # the logits oracle: the SAME module built on the reference's pure-PyTorch blocks (block_cls=) also gets the
+            # reference-style torch glue, so that arm contains nothing of ours (tests / the PyTorch-GPU comparison arm)
+            tok = torch.cat([rgb.flatten(2), ir.flatten(2)], dim=2).transpose(1, 2).contiguous()
             for layer in self.layers:
                 tok = layer(tok)
-            return ops.tokens_scatter(tok, (B, C, H, W))
-        tok = torch.cat([rgb.flatten(2), ir.flatten(2)], dim=2).transpose(1, 2).contiguous()  # same layout, plain torch glue
+            out = tok.transpose(1, 2).reshape(B, C, 2, H, W)
+            return out[:, :, 0].contiguous(), out[:, :, 1].contiguous()
+        if ir.dtype != rgb.dtype:
+            ir = ir.to(rgb.dtype)
+        tok = ops.tokens_gather(rgb, ir)  # (B, 2HW, C), VIS tokens then IR tokens: one tiled transpose (raises off-GPU)
         for layer in self.layers:
             tok = layer(tok)
-        out = tok.transpose(1, 2).reshape(B, C, 2, H, W)
-        return out[:, :, 0].contiguous(), out[:, :, 1].contiguous()
+        return ops.tokens_scatter(tok, (B, C, H, W))
 
 
 def install(ref_models=None, scan=True, pscan=True, ffm=True, fusion=False):

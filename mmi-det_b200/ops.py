@@ -49,8 +49,20 @@ def selscan_fwd_raw(x, delta, A, Bm, Cm, D, z=None, h0=None, want_state=False, w
     global launches
     lib = _lib.load()
     _require_cuda(x, "selective_scan")
+    if x.dim() != 3 or A.dim() != 2:
+        raise ValueError(f"selective_scan: x must be (B, L, ED) and A (ED, N); got {tuple(x.shape)} and {tuple(A.shape)}")
     Bsz, L, ED = x.shape
     N = A.shape[1]
+    # the C ABI takes raw pointers: every shape is checked here (the reference would raise a broadcasting error instead)
+    want = {"delta": (delta, (Bsz, L, ED)), "z": (z, (Bsz, L, ED)), "A": (A, (ED, N)), "B": (Bm, (Bsz, L, N)),
+            "C": (Cm, (Bsz, L, N)), "D": (D, (ED,)), "h0": (h0, (Bsz, ED, N))}
+    for name, (t, shp) in want.items():
+        if t is not None and tuple(t.shape) != shp:
+            raise ValueError(f"selective_scan: {name} has shape {tuple(t.shape)}, expected {shp} for x {tuple(x.shape)}")
+        if t is not None and t.device != x.device:
+            raise RuntimeError(f"selective_scan: {name} is on {t.device}, x on {x.device}")
+    if x.dtype not in _DT:
+        raise RuntimeError(f"selective_scan: unsupported dtype {x.dtype} (float32 / bfloat16 / float16)")
     dt = x.dtype
     x, delta = _rows(x), _rows(delta.to(dt))
     z = None if z is None else _rows(z.to(dt))
@@ -78,6 +90,11 @@ def selscan_bwd_raw(saved, chk, dout, flags=0):
     Bsz, L, ED = x.shape
     N = A.shape[1]
     dt = x.dtype
+    if tuple(dout.shape) != (Bsz, L, ED):
+        raise ValueError(f"selective_scan backward: dout has shape {tuple(dout.shape)}, expected {(Bsz, L, ED)}")
+    nchk = (L + lib.mmi_selscan_chunk() - 1) // lib.mmi_selscan_chunk()
+    if chk is None or tuple(chk.shape) != (Bsz, nchk, ED, N):
+        raise ValueError("selective_scan backward: checkpoints of the matching forward call are required")
     dout = _rows(dout.to(dt))
     dx, dd = torch.empty((Bsz, L, ED), dtype=dt, device=x.device), torch.empty((Bsz, L, ED), dtype=dt, device=x.device)
     dz = torch.empty((Bsz, L, ED), dtype=dt, device=x.device) if z is not None else None
@@ -96,7 +113,9 @@ def selscan_bwd_raw(saved, chk, dout, flags=0):
 class _SelectiveScan(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, delta, A, Bm, Cm, D, z, flags):
-        need = any(t is not None and t.requires_grad for t in (x, delta, A, Bm, Cm, D, z))
+        # needs_input_grad is False under torch.no_grad() / inference even for Parameters: no checkpoints are written and
+        # nothing is saved then (tensor.requires_grad would keep both alive at inference)
+        need = any(ctx.needs_input_grad[:7])
         out, _, chk, saved = selscan_fwd_raw(x, delta, A, Bm, Cm, D, z=z, want_chk=need, flags=flags)
         ctx.flags = flags
         ctx.has_z = z is not None
@@ -134,6 +153,8 @@ class _CausalConv1dSiLU(torch.autograd.Function):
         _require_cuda(x, "causal_conv1d")
         Bsz, L, ED = x.shape
         K = weight.shape[-1]
+        if weight.numel() != ED * K or (bias is not None and tuple(bias.shape) != (ED,)):
+            raise ValueError(f"causal_conv1d: weight {tuple(weight.shape)} / bias do not match a depthwise conv over {ED} channels")
         x = _rows(x)
         w = weight.detach().reshape(ED, K).float().contiguous()
         b = None if bias is None else bias.detach().float().contiguous()

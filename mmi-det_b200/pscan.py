@@ -2,8 +2,8 @@
 
 Same call: pscan(A_in, X_in) with A_in, X_in (B, L, D, N) -> H (B, L, D, N), H[t] = A[t] * H[t-1] + X[t];
 backward returns (gradA, gradX) exactly as PScan.backward (models/pscan.py:189-224).  Inputs are not modified
-(the reference clones, :167-174).  Runs on the CUDA kernels of csrc/pscan.cu through the C ABI; fp32 compute
-(other dtypes are converted on entry and the result cast back)."""
+(the reference clones, :167-174).  Runs on the CUDA kernels of csrc/pscan.cu through the C ABI: float64 inputs are scanned
+in float64, every other dtype in fp32 (converted on entry, result cast back)."""
 from __future__ import annotations
 
 import ctypes
@@ -29,17 +29,23 @@ class PScan(torch.autograd.Function):
     def forward(ctx, A_in, X_in):
         if not A_in.is_cuda:
             raise RuntimeError("mmidet_b200.pscan: CUDA tensors required (no CPU path)")
+        if A_in.shape != X_in.shape or X_in.dim() != 4:
+            raise ValueError(f"pscan: A_in and X_in must both be (B, L, D, N); got {tuple(A_in.shape)} and {tuple(X_in.shape)}")
         lib = _lib.load()
         B, L, D, N = X_in.shape
-        A = A_in.detach().float().contiguous()
-        X = X_in.detach().float().contiguous()
+        # the reference is dtype-generic (models/pscan.py:37-92): float64 inputs are scanned in float64, everything else in fp32
+        f64 = X_in.dtype == torch.float64 or A_in.dtype == torch.float64
+        wd = torch.float64 if f64 else torch.float32
+        A = A_in.detach().to(wd).contiguous()
+        X = X_in.detach().to(wd).contiguous()
         H = torch.empty_like(X)
         ws = _ws(lib, B, L, D, N, X.device)
-        _lib.check(lib.mmi_pscan_fwd(_ops._ptr(A), _ops._ptr(X), _ops._ptr(H), _ops._ptr(ws), B, L, D, N,
-                                     _ops._stream(X)), "mmi_pscan_fwd")
+        fn = lib.mmi_pscan_fwd_f64 if f64 else lib.mmi_pscan_fwd
+        _lib.check(fn(_ops._ptr(A), _ops._ptr(X), _ops._ptr(H), _ops._ptr(ws), B, L, D, N, _ops._stream(X)), "mmi_pscan_fwd")
         _ops.launches += 2
         ctx.save_for_backward(A, H)
         ctx.dtypes = (A_in.dtype, X_in.dtype)
+        ctx.f64 = f64
         return H.to(X_in.dtype)
 
     @staticmethod
@@ -47,11 +53,12 @@ class PScan(torch.autograd.Function):
         lib = _lib.load()
         A, H = ctx.saved_tensors
         B, L, D, N = H.shape
-        g = grad_output_in.float().contiguous()
+        g = grad_output_in.to(H.dtype).contiguous()
         gA, gX = torch.empty_like(H), torch.empty_like(H)
         ws = _ws(lib, B, L, D, N, H.device)
-        _lib.check(lib.mmi_pscan_bwd(_ops._ptr(A), _ops._ptr(H), _ops._ptr(g), _ops._ptr(gA), _ops._ptr(gX),
-                                     _ops._ptr(ws), B, L, D, N, _ops._stream(H)), "mmi_pscan_bwd")
+        fn = lib.mmi_pscan_bwd_f64 if ctx.f64 else lib.mmi_pscan_bwd
+        _lib.check(fn(_ops._ptr(A), _ops._ptr(H), _ops._ptr(g), _ops._ptr(gA), _ops._ptr(gX), _ops._ptr(ws), B, L, D, N,
+                      _ops._stream(H)), "mmi_pscan_bwd")
         _ops.launches += 2
         return gA.to(ctx.dtypes[0]), gX.to(ctx.dtypes[1])
 

@@ -106,15 +106,46 @@ def gen_block():
     save("mamba_block", x=x, y_mixer=y_mixer, y_res=y_res, g=g, gx=gx, **arrs)
 
 
+def gen_step():
+    """MambaBlock.step / ssm_step (models/mamba.py:289-353) through ResidualBlock.step over 8 tokens from the empty cache,
+    next to forward() on the same 8-token prefix (the two must agree: recurrent == parallel form)."""
+    torch.manual_seed(4)
+    cfg = MambaConfig(d_model=16, n_layers=1)
+    blk = ResidualBlock(cfg).eval()
+    with torch.no_grad():
+        blk.mixer.A_log.add_(torch.randn_like(blk.mixer.A_log) * 0.3)  # leave the S4D-real init: general-A path too
+        blk.mixer.D.normal_(1.0, 0.2)
+    B, T = 3, 8
+    x = torch.randn(B, T, 16)
+    cache = (None, torch.zeros(B, cfg.d_inner, cfg.d_conv - 1))
+    ys, hs = [], []
+    with torch.no_grad():
+        for t in range(T):
+            y, cache = blk.step(x[:, t], cache)
+            ys.append(y)
+            hs.append(cache[0])
+        y_fwd = blk(x)
+    arrs = {"sd." + k: v for k, v in blk.state_dict().items()}
+    save("mamba_step", x=x, y_step=torch.stack(ys, 1), h_step=torch.stack(hs, 1), inputs_last=cache[1], y_fwd=y_fwd, **arrs)
+
+
 def gen_ffm():
     """extract_frequency2 at the sizes SURVEY F3 probed (negative-slice quirk) + fourier_transform + Seperation_loss."""
-    for hw in (8, 16, 20, 7, (8, 12)):
+    for hw in (8, 16, 20, 7, (8, 12), 80, 160, (96, 72)):
         h, w = (hw, hw) if isinstance(hw, int) else hw
         g = torch.Generator().manual_seed(h * 100 + w)
-        img = torch.randn(2, 3, h, w, generator=g)
+        big = max(h, w) > 64
+        img = torch.randn(1 if big else 2, 2 if big else 3, h, w, generator=g)
         low, high = C.extract_frequency2(img)
         fs = C.fourier_transform(img)
-        save(f"ffm_{h}x{w}", img=img, low=low, high=high, fs_re=fs.real, fs_im=fs.imag)
+        extra = {}
+        if h == w and h in (8, 80):  # extract_frequency (common.py:72-93, no caller in the reference): fixed threshold 30
+            lo1, hi1 = C.extract_frequency(img)
+            extra = dict(ef_low=lo1.float(), ef_high=hi1.float())
+        if big:  # keep the large fixtures small: spectrum omitted (fourier_transform is pinned at the small sizes)
+            save(f"ffm_{h}x{w}", img=img.half(), low=low, high=high, **extra)
+        else:
+            save(f"ffm_{h}x{w}", img=img, low=low, high=high, fs_re=fs.real, fs_im=fs.imag, **extra)
     g = torch.Generator().manual_seed(9)
     M = torch.rand(36, 64, generator=g)
     save("seploss", M=M, loss=C.Seperation_loss(M))
@@ -215,6 +246,6 @@ def gen_pattern():
 
 if __name__ == "__main__":
     torch.set_num_threads(4)
-    todo = sys.argv[1:] or ["pscan", "selscan", "block", "ffm", "fusion", "detector", "pattern"]
+    todo = sys.argv[1:] or ["pscan", "selscan", "block", "step", "ffm", "fusion", "detector", "pattern"]
     for name in todo:
         globals()["gen_" + name]()

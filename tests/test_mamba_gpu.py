@@ -130,7 +130,7 @@ def test_causal_conv1d_silu_vs_oracle(shape, K, dtype, tol):
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
-@pytest.mark.parametrize("rows,C", [(7, 8), (130, 256), (33, 1000), (5, 1024)])
+@pytest.mark.parametrize("rows,C", [(7, 8), (130, 256), (33, 1000), (5, 1024), (19, 1280), (9, 2560), (3, 4096), (11, 1032)])
 def test_rmsnorm_vs_torch_fp64(rows, C, dtype, tol):
     """fused RMSNorm (models/mamba.py:356-366) forward, dx and dw vs the reference formula evaluated in fp64."""
     from mmidet_b200 import ops
@@ -233,7 +233,7 @@ def test_conv_and_rmsnorm_stay_inside_their_outputs(dtype):
         _lib.check(lib.mmi_causal_conv1d_fwd(P(x), P(w), P(b), P(y), B, L, ED, 4, ED, ED, DT[dtype], 1, ST(x)), "conv fwd")
         _lib.check(lib.mmi_causal_conv1d_bwd(P(x), P(w), P(b), P(gy), P(dx), P(dw), P(db), B, L, ED, 4, ED, ED, ED, DT[dtype], 1, ST(x)),
                    "conv bwd")
-    for (rows, C) in [(77, 72), (1, 8), (4097, 256), (130, 1024)]:
+    for (rows, C) in [(77, 72), (1, 8), (4097, 256), (130, 1024), (21, 1280), (9, 2568)]:
         x, g = torch.randn(rows, C, device="cuda").to(dtype), torch.randn(rows, C, device="cuda").to(dtype)
         w = torch.rand(C, device="cuda") + 0.5
         y, dx, dw = carve(rows * C, dtype), carve(rows * C, dtype), carve(C, torch.float32)
@@ -243,3 +243,64 @@ def test_conv_and_rmsnorm_stay_inside_their_outputs(dtype):
     for i, (buf, n) in enumerate(arenas):
         assert bool((buf[:GUARD] == 7).all()) and bool((buf[GUARD + n:] == 7).all()), f"guard band of arena {i} overwritten"
         assert bool(torch.isfinite(buf[GUARD:GUARD + n].float()).all())
+
+
+def test_step_matches_reference_and_forward(golden):
+    """MambaBlock.step / ssm_step (models/mamba.py:289-353) through ResidualBlock.step over 8 tokens from the empty cache
+    (h = None, zero conv window): outputs, the state after every token and the final conv window against the unmodified
+    reference, and against our own forward() on the same prefix (recurrent form == parallel form).  General (trained) A."""
+    from mmidet_b200.mamba import MambaConfig, ResidualBlock
+    g = golden("mamba_step")
+    cfg = MambaConfig(d_model=16, n_layers=1)
+    blk = ResidualBlock(cfg)
+    _load_sd(blk, g, "sd.")
+    blk = blk.cuda().eval()
+    x = torch.from_numpy(g["x"]).cuda()
+    B, T, _ = x.shape
+    cache = (None, torch.zeros(B, cfg.d_inner, cfg.d_conv - 1, device="cuda"))
+    ys, hs = [], []
+    with torch.no_grad():
+        for t in range(T):
+            y, cache = blk.step(x[:, t], cache)
+            ys.append(y)
+            hs.append(cache[0])
+        y_fwd = blk(x)
+    y_step = torch.stack(ys, 1).cpu().numpy()
+    assert relerr(y_step, g["y_step"]) <= TOL32
+    assert relerr(torch.stack(hs, 1).cpu().numpy(), g["h_step"]) <= TOL32
+    assert relerr(cache[1].cpu().numpy(), g["inputs_last"]) <= 1e-6
+    assert relerr(y_fwd.cpu().numpy(), g["y_fwd"]) <= TOL32
+    assert relerr(y_step, y_fwd.cpu().numpy()) <= TOL32
+
+
+def test_no_eager_fallbacks():
+    """shapes outside the kernels raise instead of running stock torch: d_conv > 4, an RMSNorm width that is not a multiple
+    of 8, CPU tensors through the fusion block."""
+    from mmidet_b200.mamba import MambaBlock, MambaConfig, MambaFusion, RMSNorm
+    blk = MambaBlock(MambaConfig(d_model=16, n_layers=1, d_conv=5)).cuda()
+    with pytest.raises(RuntimeError):
+        blk(torch.randn(1, 8, 16, device="cuda"))
+    with pytest.raises(RuntimeError):
+        RMSNorm(12).cuda()(torch.randn(2, 3, 12, device="cuda"))
+    with pytest.raises(RuntimeError):
+        MambaFusion(16)([torch.randn(1, 16, 4, 4), torch.randn(1, 16, 4, 4)])
+
+
+def test_inference_skips_checkpoints():
+    """under torch.no_grad() (eval / Graphed inference) the forward neither writes checkpoints nor saves tensors, even though
+    A_log / D are Parameters with requires_grad=True: peak memory stays below the checkpoint size."""
+    from mmidet_b200 import ops
+    B, L, ED, N = 2, 3200, 256, 16
+    x, delta = torch.randn(B, L, ED, device="cuda"), torch.rand(B, L, ED, device="cuda") * 0.1
+    A = torch.nn.Parameter(-torch.arange(1, N + 1, device="cuda", dtype=torch.float32).repeat(ED, 1))
+    D = torch.nn.Parameter(torch.ones(ED, device="cuda"))
+    Bm, Cm = torch.randn(B, L, N, device="cuda"), torch.randn(B, L, N, device="cuda")
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    with torch.no_grad():
+        y = ops.selective_scan(x, delta, A, Bm, Cm, D)
+    torch.cuda.synchronize()
+    chk_bytes = B * (L // 16) * ED * N * 4
+    assert y.grad_fn is None
+    assert torch.cuda.max_memory_allocated() - base < y.numel() * 4 + chk_bytes // 2

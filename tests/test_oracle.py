@@ -85,17 +85,39 @@ def test_mamba_block_matches_reference(golden):
     assert relerr(yr, g["y_res"]) <= 1e-5
 
 
-@pytest.mark.parametrize("tag", ["8x8", "16x16", "20x20", "7x7", "8x12"])
+def test_step_matches_forward_and_reference(golden):
+    """MambaBlock.step / ssm_step (mamba.py:289-353): the recurrent form over 8 tokens == forward() on the same prefix
+    (reference outputs), and the oracle's block restatement reproduces both."""
+    g = golden("mamba_step")
+    assert relerr(g["y_step"], g["y_fwd"]) <= 1e-5
+    p = {k[len("sd.mixer."):]: v for k, v in g.items() if k.startswith("sd.mixer.")}
+    y = O.mamba_block_forward(O.rmsnorm(g["x"], g["sd.norm.weight"]), p) + g["x"]
+    assert relerr(y, g["y_step"]) <= 1e-5
+
+
+@pytest.mark.parametrize("tag", ["8x8", "80x80"])
+def test_extract_frequency_matches_reference(golden, tag):
+    """extract_frequency (common.py:72-93; no caller in the reference): fixed threshold 30, complex -> real -> fp16."""
+    g = golden(f"ffm_{tag}")
+    lo, hi = O.extract_frequency(g["img"].astype(np.float32))
+    scale = max(float(np.max(np.abs(g["ef_high"]))), 1e-6)
+    assert np.max(np.abs(np.asarray(lo, np.float32) - g["ef_low"])) <= 2e-3 * scale
+    assert np.max(np.abs(np.asarray(hi, np.float32) - g["ef_high"])) <= 2e-3 * scale
+
+
+@pytest.mark.parametrize("tag", ["8x8", "16x16", "20x20", "7x7", "8x12", "80x80", "160x160", "96x72"])
 def test_ffm_matches_reference(golden, tag):
     """extract_frequency2 incl. the negative-slice wrap (common.py:44-56) and the fp16 real cast (:66-67)."""
     g = golden(f"ffm_{tag}")
+    g["img"] = g["img"].astype(np.float32)
     low, high = O.extract_frequency2(g["img"])
     assert low.dtype == np.float16 and high.dtype == np.float16
     # fp16 outputs: allow 1 fp16 ulp of the largest magnitude (pocketfft vs numpy fft rounding)
     assert relerr(low, g["low"]) <= 2e-3
     assert relerr(high, g["high"]) <= 2e-3
-    fs = O.fourier_transform(g["img"])
-    assert relerr(fs.real, g["fs_re"]) <= 1e-5 and relerr(fs.imag, g["fs_im"]) <= 1e-5
+    if "fs_re" in g:
+        fs = O.fourier_transform(g["img"])
+        assert relerr(fs.real, g["fs_re"]) <= 1e-5 and relerr(fs.imag, g["fs_im"]) <= 1e-5
     # mask restatement == slice restatement
     kh, kl = O.ffm_masks(*g["img"].shape[-2:])
     fsh = np.fft.fftshift(np.fft.fftn(g["img"], axes=(-2, -1)), axes=(-2, -1))

@@ -45,6 +45,85 @@ def test_pscan_vs_oracle_multi_segment(shape):
     assert relerr(gX.cpu().numpy(), gX64) <= 1e-4
 
 
+def test_pscan_fp64_vs_reference_golden(golden):
+    """models/pscan.py is dtype-generic: float64 inputs are scanned in float64 (fixture from the reference's own fp64 run)."""
+    from mmidet_b200.pscan import pscan
+    g = golden("pscan_f64")
+    A, X = _t(g["A"]).requires_grad_(True), _t(g["X"]).requires_grad_(True)
+    assert A.dtype == torch.float64
+    H = pscan(A, X)
+    gA, gX = torch.autograd.grad(H, (A, X), _t(g["gH"]))
+    assert H.dtype == torch.float64 and gA.dtype == torch.float64
+    assert relerr(H.detach().cpu().numpy(), g["H"]) <= 1e-12
+    assert relerr(gA.cpu().numpy(), g["gA"]) <= 1e-12
+    assert relerr(gX.cpu().numpy(), g["gX"]) <= 1e-12
+
+
+def test_pscan_fp64_multi_segment():
+    from mmidet_b200.pscan import pscan
+    rng = np.random.default_rng(3)
+    shape = (2, 1500, 12, 16)
+    A = rng.random(shape) * 0.5 + 0.5
+    X = rng.standard_normal(shape)
+    gH = rng.standard_normal(shape)
+    At, Xt = _t(A).requires_grad_(True), _t(X).requires_grad_(True)
+    H = pscan(At, Xt)
+    gA, gX = torch.autograd.grad(H, (At, Xt), _t(gH))
+    H64 = O.pscan_seq_fwd(A, X)
+    gA64, gX64 = O.pscan_seq_bwd(A, H64, gH)
+    assert relerr(H.detach().cpu().numpy(), H64) <= 1e-12
+    assert relerr(gA.cpu().numpy(), gA64) <= 1e-12 and relerr(gX.cpu().numpy(), gX64) <= 1e-12
+
+
+@pytest.mark.parametrize("tag", ["80x80", "160x160", "96x72"])
+def test_ffm_large_maps_vs_reference_golden(golden, tag):
+    """extract_frequency2 above 64 x 64 (H in {8, 16, 20, 80, 160}): the kept-bin projection kernel
+    against outputs of the unmodified reference; fp16 outputs, one fp16 ulp of the largest magnitude allowed."""
+    from mmidet_b200.ffm import extract_frequency2
+    g = golden(f"ffm_{tag}")
+    img = _t(g["img"].astype(np.float32))
+    low, high, prod = extract_frequency2(img, with_product=True)
+    assert low.dtype == torch.float16 and high.dtype == torch.float16 and low.shape == img.shape
+    assert relerr(low.float().cpu().numpy(), g["low"].astype(np.float32)) <= 2e-3
+    assert relerr(high.float().cpu().numpy(), g["high"].astype(np.float32)) <= 2e-3
+    assert relerr(prod.cpu().numpy(), high.float().cpu().numpy() * g["img"].astype(np.float32)) <= 1e-6
+    lo16, hi16 = extract_frequency2(img.half())  # fp16 callers (detect_twostream.py:45 model.half())
+    assert relerr(lo16.float().cpu().numpy(), g["low"].astype(np.float32)) <= 4e-3
+
+
+@pytest.mark.parametrize("tag", ["8x8", "16x16", "20x20", "8x12"])
+def test_fourier_transform_vs_reference_golden(golden, tag):
+    """fourier_transform (models/common.py:25-32) on the device against the reference's spectrum."""
+    from mmidet_b200.ffm import fourier_transform
+    g = golden(f"ffm_{tag}")
+    fs = fourier_transform(_t(g["img"]))
+    assert relerr(fs.real.cpu().numpy(), g["fs_re"]) <= 1e-5 and relerr(fs.imag.cpu().numpy(), g["fs_im"]) <= 1e-5
+
+
+@pytest.mark.parametrize("tag", ["8x8", "80x80"])
+def test_extract_frequency_vs_reference_golden(golden, tag):
+    """extract_frequency (models/common.py:72-93, no caller in the reference): fixed threshold 30, spectra cast to fp16."""
+    from mmidet_b200.ffm import extract_frequency
+    g = golden(f"ffm_{tag}")
+    lo, hi = extract_frequency(_t(g["img"].astype(np.float32)))
+    assert lo.dtype == torch.float16 and hi.dtype == torch.float16
+    scale = max(float(np.max(np.abs(g["ef_high"]))), 1e-6)
+    assert np.max(np.abs(lo.float().cpu().numpy() - g["ef_low"])) <= 2e-3 * scale
+    assert np.max(np.abs(hi.float().cpu().numpy() - g["ef_high"])) <= 2e-3 * scale
+
+
+def test_ffm_helpers_refuse_silent_zero_gradients():
+    """the value-only drop-ins raise when asked to differentiate instead of returning no grad_fn."""
+    from mmidet_b200.ffm import extract_frequency2, separation_loss
+    img = torch.randn(1, 2, 8, 8, device="cuda", requires_grad=True)
+    with pytest.raises(RuntimeError):
+        extract_frequency2(img)
+    with torch.no_grad():
+        extract_frequency2(img)
+    with pytest.raises(RuntimeError):
+        separation_loss(torch.rand(6, 64, device="cuda", requires_grad=True))
+
+
 @pytest.mark.parametrize("tag", ["8x8", "16x16", "20x20", "7x7", "8x12"])
 def test_ffm_vs_reference_golden(golden, tag):
     """extract_frequency2 incl. the negative-slice quirk; fp16 outputs may differ by one fp16 ulp."""

@@ -384,3 +384,51 @@ def test_scan_kernels_stay_inside_their_outputs(shape, dtype):
         assert bool((buf[:GUARD] == 7).all()) and bool((buf[GUARD + n:] == 7).all()), f"guard band of arena {i} overwritten"
     for t in (out, dx, dd, dz, dA, dD, dB, dC):
         assert bool(torch.isfinite(t.float()).all())
+
+
+@pytest.mark.parametrize("random_A", [False, True])
+@pytest.mark.parametrize("L", [83, 130, 5])
+def test_final_state_with_fused_softplus_and_ragged_L(L, random_A):
+    """want_state + MMI_FLAG_DELTA_SOFTPLUS + L not a multiple of the super-tile.  The rows past L that the TMA
+    engine zero-fills must stay identity steps (softplus(0) = ln 2 would decay the state): hT == h[L-1] of the oracle, and
+    h0 -> hT chaining over a cut equals one call."""
+    from mmidet_b200 import _lib, ops
+    B, ED = 2, 40
+    inp = scan_inputs(B, L, ED, seed=L, random_A=random_A)
+    rng = np.random.default_rng(L)
+    pre = (rng.standard_normal((B, L, ED)) * 1.5 - 2.0).astype(np.float32)
+    sp = np.log1p(np.exp(pre.astype(np.float64)))
+    a = {k: _t(v) for k, v in inp.items()}
+    tpre = _t(pre)
+    fl = _lib.FLAG_DELTA_SOFTPLUS
+    out, hT, _, _ = ops.selscan_fwd_raw(a["x"], tpre, a["A"], a["Bm"], a["Cm"], a["D"], z=a["z"], want_state=True, flags=fl)
+    ref_out, ref_h = O.selective_scan_fwd(inp["x"], sp, inp["A"], inp["Bm"], inp["Cm"], inp["D"], z=inp["z"],
+                                          dtype=np.float64, return_state=True)
+    assert relerr(out.cpu().numpy(), ref_out) <= TOL32
+    assert relerr(hT.cpu().numpy(), ref_h) <= TOL32
+    cut = L // 2
+    sl = lambda t, s: t[:, s].contiguous()
+    _, h1, _, _ = ops.selscan_fwd_raw(sl(a["x"], slice(0, cut)), sl(tpre, slice(0, cut)), a["A"], sl(a["Bm"], slice(0, cut)),
+                                      sl(a["Cm"], slice(0, cut)), a["D"], want_state=True, flags=fl)
+    _, h2, _, _ = ops.selscan_fwd_raw(sl(a["x"], slice(cut, L)), sl(tpre, slice(cut, L)), a["A"], sl(a["Bm"], slice(cut, L)),
+                                      sl(a["Cm"], slice(cut, L)), a["D"], h0=h1, want_state=True, flags=fl)
+    assert relerr(h2.cpu().numpy(), ref_h) <= TOL32
+
+
+def test_shape_mismatches_raise_before_the_call():
+    """the C ABI takes raw pointers, so the operator validates every shape first."""
+    from mmidet_b200 import ops
+    dev = "cuda"
+    x = torch.randn(2, 32, 16, device=dev)
+    A, D = -torch.rand(16, 16, device=dev), torch.ones(16, device=dev)
+    Bm = torch.randn(2, 32, 16, device=dev)
+    with pytest.raises(ValueError):
+        ops.selective_scan(x, x[:, :31], A, Bm, Bm, D)
+    with pytest.raises(ValueError):
+        ops.selective_scan(x, x, A, Bm[:1], Bm, D)  # a broadcast (1, L, N) B
+    with pytest.raises(ValueError):
+        ops.selective_scan(x, x, A[:8], Bm, Bm, D)
+    with pytest.raises(ValueError):
+        ops.selective_scan(x, x, A, Bm, Bm, D[:8])
+    with pytest.raises(ValueError):
+        ops.selective_scan(x, x, A, Bm, Bm, D, z=x[..., :8])
