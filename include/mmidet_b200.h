@@ -209,6 +209,27 @@ int mmi_selscan_fwd_bwd_host(const void *x, const void *delta, const void *z, co
                              int dtype, int flags);
 void mmi_host_workspace_free(void);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Detector input / post-processing.
+ * mmi_u8_split_normalize replaces `imgs.float() / 255.0; imgs[:, :3]; imgs[:, 3:]` (train.py:743-745,
+ *   detect_twostream.py:74-85): imgs_u8 (B, 6, H, W) uint8 -> rgb, ir (B, 3, H, W) dtype, one pass.
+ * mmi_detect_decode replaces the inference branch of Detect.forward for one level (models/yolo_test.py:47-68):
+ *   x (bs, na*no, ny, nx) dtype [the 1x1 conv output] -> raw (bs, na, ny, nx, no) (nullable) and the decoded rows
+ *   [row_off, row_off + na*ny*nx) of pred (bs, rows_total, no); anchor_wh (na, 2) fp32 = anchor_grid of the level.
+ * mmi_nms_candidates + (caller sorts `key` ascending, stable -> order; start = exclusive prefix sum of count) +
+ * mmi_nms_suppress replace non_max_suppression (utils/general.py:486-580, best-class branch) for the whole batch:
+ *   pred (bs, rows_per_img, no) dtype; det (bs*rows_per_img, 6) fp32 = xyxy, conf, cls of the candidate rows;
+ *   key (bs*rows_per_img) fp64; count (bs) int32; order int64 row indices sorted by key; mask scratch of
+ *   total_candidates * ceil(min(max_count, max_nms) / 64) * 8 bytes; keep (bs, max_det) int64 row indices into det,
+ *   nkeep (bs) int32.  max_wh is the class offset of :563 (4096). */
+int mmi_u8_split_normalize(const void *imgs_u8, void *rgb, void *ir, int B, int H, int W, int dtype, void *stream);
+int mmi_detect_decode(const void *x, void *raw, void *pred, int bs, int na, int no, int ny, int nx, float stride,
+                      const float *anchor_wh, int64_t rows_total, int64_t row_off, int dtype, void *stream);
+int mmi_nms_candidates(const void *pred, float *det, double *key, int *count, int bs, int64_t rows_per_img, int no,
+                       float conf_thres, int dtype, void *stream);
+int mmi_nms_suppress(const float *det, const int64_t *order, const int *start, const int *count, void *mask, int64_t *keep,
+                     int *nkeep, int bs, int max_count, int max_nms, int max_det, float iou_thres, float max_wh, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

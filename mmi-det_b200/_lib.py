@@ -106,6 +106,10 @@ _SIGNATURES = {
     "mmi_rmsnorm_bwd": (_i, [_vp] * 5 + [_i64, _i, _i64, _i64, _i64, _c.c_float, _i, _i, _vp]),
     "mmi_tokens_gather": (_i, [_vp] * 3 + [_i] * 4 + [_vp]),
     "mmi_tokens_scatter": (_i, [_vp] * 3 + [_i] * 4 + [_vp]),
+    "mmi_u8_split_normalize": (_i, [_vp] * 3 + [_i] * 4 + [_vp]),
+    "mmi_detect_decode": (_i, [_vp] * 3 + [_i] * 5 + [_c.c_float, _vp, _i64, _i64, _i, _vp]),
+    "mmi_nms_candidates": (_i, [_vp] * 4 + [_i, _i64, _i, _c.c_float, _i, _vp]),
+    "mmi_nms_suppress": (_i, [_vp] * 7 + [_i] * 4 + [_c.c_float, _c.c_float, _vp]),
     "mmi_selscan_fwd_bwd_host": (_i, [_vp] * 16 + [_i] * 6),
     "mmi_host_workspace_free": (None, []),
 }

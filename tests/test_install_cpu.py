@@ -68,3 +68,22 @@ def test_fusion_contract_shapes_on_meta():
     assert fus.n_embd == 32 and len(fus.layers) == 1
     names = {k.split(".")[3] for k in fus.state_dict() if k.startswith("layers.0.mixer.")}
     assert names >= {"A_log", "D", "in_proj", "conv1d", "x_proj", "dt_proj", "out_proj"}
+
+
+def test_staged_reference_is_unmodified():
+    """baseline/_ref (what travels to the GPU box) is byte-for-byte the reference: every staged file equals its source
+    under /root/reference and the manifest matches.  Skipped where either side is absent."""
+    import hashlib
+    import os
+    import pytest
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dst, src = os.path.join(root, "baseline", "_ref"), os.environ.get("MMIDET_REF", "/root/reference")
+    if not os.path.isdir(dst):
+        pytest.skip("no staged reference")
+    lines = [l.split("  ", 1) for l in open(os.path.join(dst, "MANIFEST.sha256")).read().splitlines()]
+    assert len(lines) > 20
+    for digest, rel in lines:
+        data = open(os.path.join(dst, rel), "rb").read()
+        assert hashlib.sha256(data).hexdigest() == digest, rel
+        if os.path.isdir(src):
+            assert data == open(os.path.join(src, rel), "rb").read(), rel
