@@ -63,7 +63,9 @@ __global__ void __launch_bounds__(256) u8_split_kernel(const uint8_t *__restrict
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
     float f[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) f[k] = float((w[k >> 2] >> (8 * (k & 3))) & 0xffu) / 255.0f;  // same rounding as x.float() / 255
+    // torch divides a tensor by a Python scalar as a multiplication by the fp32 reciprocal (ATen div_true_kernel): same bits
+    constexpr float kInv255 = 1.0f / 255.0f;
+    for (int k = 0; k < 16; ++k) f[k] = float((w[k >> 2] >> (8 * (k & 3))) & 0xffu) * kInv255;
     st16<T>((m ? ir : rgb) + b * n3 + off, f);
 }
 template <typename T>
@@ -72,7 +74,7 @@ __global__ void __launch_bounds__(256) u8_split_scalar_kernel(const uint8_t *__r
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int64_t blk = i / n3, off = i % n3;
-    ((blk & 1) ? ir : rgb)[(blk >> 1) * n3 + off] = from_f32<T>(float(src[i]) / 255.0f);
+    ((blk & 1) ? ir : rgb)[(blk >> 1) * n3 + off] = from_f32<T>(float(src[i]) * (1.0f / 255.0f));
 }
 
 int u8_split_launch(const void *src, void *rgb, void *ir, int B, int64_t HW, int dtype, cudaStream_t st) {

@@ -39,6 +39,37 @@ struct BwdParams {
     float *seg_ws;  // (B, nseg, ED, N + 1): a*g leaving the segment when nothing enters it | sum of delta
 };
 
+// second-generation kernels (selscan_fwd2.cu / selscan_bwd2.cu): persistent grid, items = (chain, L segment) handed out by
+// ticket in dependency order; a chain = one batch element x 32 channels
+struct SegSched {
+    int nseg, seg_tiles;   // L segments per chain, super-tiles per segment
+    int ntile_c, nchains;  // channel tiles per batch element, B * ntile_c
+    int nitems;            // nchains * nseg
+    unsigned *ticket;      // [1] item counter
+    unsigned *done;        // [nchains] number of finished segments of the chain
+    float *carry;          // [nchains][8][32] float2: state (forward) / a*g (backward) handed to the next segment
+};
+struct Bwd2Params {
+    BwdParams b;
+    SegSched s;
+};
+struct Fwd2Params {
+    FwdParams f;
+    SegSched s;
+};
+
+// first generation (look-back L split for small grids) and second generation entry points; selscan_*_launch dispatch
+int selscan_fwd1_launch(const FwdParams &p, int dtype, void *ws, cudaStream_t st);
+int64_t selscan_fwd1_ws_bytes(int B, int ED);
+int selscan_bwd1_launch(BwdParams p, int dtype, void *ws, cudaStream_t st);
+int64_t selscan_bwd1_ws_bytes(int B, int L, int ED);
+int selscan_fwd2_launch(const FwdParams &p, int dtype, void *ws, cudaStream_t st);
+int64_t selscan_fwd2_ws_bytes(int B, int L, int ED);
+int selscan_bwd2_launch(const BwdParams &p, int dtype, void *ws, cudaStream_t st);
+int64_t selscan_bwd2_ws_bytes(int B, int L, int ED);
+bool selscan_use_v2(int B, int L, int ED, int flags);  // which generation a call takes (shape heuristic, MMI_FLAG_CFG override)
+int seg_sched_plan(int B, int L, int ED, int flags, SegSched *s);  // fills nseg / seg_tiles / ntile_c / nchains / nitems
+
 int selscan_fwd_launch(const FwdParams &p, int dtype, void *ws, cudaStream_t st);
 int64_t selscan_fwd_ws_bytes(int B, int ED);
 int selscan_bwd_launch(BwdParams p, int dtype, void *ws, cudaStream_t st);

@@ -286,21 +286,26 @@ def test_no_eager_fallbacks():
         MambaFusion(16)([torch.randn(1, 16, 4, 4), torch.randn(1, 16, 4, 4)])
 
 
-def test_inference_skips_checkpoints():
+def test_inference_skips_checkpoints(monkeypatch):
     """under torch.no_grad() (eval / Graphed inference) the forward neither writes checkpoints nor saves tensors, even though
-    A_log / D are Parameters with requires_grad=True: peak memory stays below the checkpoint size."""
+    A_log / D are Parameters with requires_grad=True; with grad enabled it does both."""
     from mmidet_b200 import ops
-    B, L, ED, N = 2, 3200, 256, 16
+    B, L, ED, N = 2, 320, 64, 16
     x, delta = torch.randn(B, L, ED, device="cuda"), torch.rand(B, L, ED, device="cuda") * 0.1
     A = torch.nn.Parameter(-torch.arange(1, N + 1, device="cuda", dtype=torch.float32).repeat(ED, 1))
     D = torch.nn.Parameter(torch.ones(ED, device="cuda"))
     Bm, Cm = torch.randn(B, L, N, device="cuda"), torch.randn(B, L, N, device="cuda")
-    torch.cuda.synchronize()
-    torch.cuda.reset_peak_memory_stats()
-    base = torch.cuda.memory_allocated()
+    seen = []
+    real = ops.selscan_fwd_raw
+
+    def spy(*a, **k):
+        seen.append(k.get("want_chk"))
+        return real(*a, **k)
+
+    monkeypatch.setattr(ops, "selscan_fwd_raw", spy)
     with torch.no_grad():
         y = ops.selective_scan(x, delta, A, Bm, Cm, D)
-    torch.cuda.synchronize()
-    chk_bytes = B * (L // 16) * ED * N * 4
-    assert y.grad_fn is None
-    assert torch.cuda.max_memory_allocated() - base < y.numel() * 4 + chk_bytes // 2
+    assert y.grad_fn is None and seen == [False]
+    y2 = ops.selective_scan(x, delta, A, Bm, Cm, D)
+    assert y2.grad_fn is not None and seen == [False, True]
+    assert torch.equal(y, y2.detach())
