@@ -697,7 +697,7 @@ static size_t al256(size_t v) { return (v + 255) & ~size_t(255); }
 // L is only split when the unsplit grid leaves at least half of the SMs idle (also applied to a forced count), so the
 // per-segment workspaces are sized for kBwdMaxSeg segments only in that case
 static int bwd_seg_cap(int B, int ntile_c) { return int64_t(B) * ntile_c * 2 <= sm_count() ? kBwdMaxSeg : 1; }
-int64_t selscan_bwd_ws_bytes(int B, int L, int ED) {
+int64_t selscan_bwd1_ws_bytes(int B, int L, int ED) {
     const int64_t ntile = (ED + 63) / 64;
     const int cap = bwd_seg_cap(B, int(ntile));
     return int64_t(al256(size_t(B) * L * ntile * 2 * kN * 4)) + int64_t(al256(size_t(B) * cap * kBwdWT * ED * (kN + 1) * 4)) +
@@ -768,7 +768,7 @@ template <typename T> static int launch_bwd_t(BwdParams p, int dtype, void *ws, 
     return check_cuda(cudaGetLastError(), "selscan_bwd finish launch");
 }
 
-int selscan_bwd_launch(BwdParams p, int dtype, void *ws, cudaStream_t st) {
+int selscan_bwd1_launch(BwdParams p, int dtype, void *ws, cudaStream_t st) {
     switch (dtype) {
         case MMI_F32: return launch_bwd_t<float>(p, dtype, ws, st);
         case MMI_BF16: return launch_bwd_t<__nv_bfloat16>(p, dtype, ws, st);

@@ -1,0 +1,35 @@
+// selscan_dispatch.cu -- which generation of the scan kernels a call takes.
+//
+//   second generation (selscan_fwd2.cu / selscan_bwd2.cu): persistent grid over (32-channel chain, L segment) items; needs
+//       enough independent chains to occupy the GPU -- the training shapes (B * ceil(ED / 32) >= half the SMs)
+//   first generation (selscan_fwd.cu / selscan_bwd.cu): one CTA per 32 / 64-channel tile, L split across CTAs with published
+//       segment summaries (decoupled look-back) -- small batches and inference, where only splitting L can fill the GPU
+// MMI_FLAG_CFG bits: 8 forces the second generation, 9 the first, 1..6 are first-generation CTA shapes (tuning / tests).
+#include <algorithm>
+
+#include "../../include/mmidet_b200.h"
+#include "common.cuh"
+#include "selscan.h"
+
+namespace mmi {
+
+bool selscan_use_v2(int B, int L, int ED, int flags) {
+    const int cfg = (flags & MMI_FLAG_CFG_MASK) >> MMI_FLAG_CFG_SHIFT;
+    if (cfg == 8) return true;
+    if (cfg != 0) return false;
+    (void)L;
+    const int64_t chains = int64_t(B) * ((ED + 31) / 32);
+    return chains * 2 >= sm_count();
+}
+
+int64_t selscan_bwd_ws_bytes(int B, int L, int ED) { return std::max(selscan_bwd1_ws_bytes(B, L, ED), selscan_bwd2_ws_bytes(B, L, ED)); }
+int64_t selscan_fwd_ws_bytes(int B, int ED) { return selscan_fwd1_ws_bytes(B, ED); }
+
+int selscan_bwd_launch(BwdParams p, int dtype, void *ws, cudaStream_t st) {
+    if (selscan_use_v2(p.B, p.L, p.ED, p.flags)) return selscan_bwd2_launch(p, dtype, ws, st);
+    return selscan_bwd1_launch(p, dtype, ws, st);
+}
+
+int selscan_fwd_launch(const FwdParams &p, int dtype, void *ws, cudaStream_t st) { return selscan_fwd1_launch(p, dtype, ws, st); }
+
+}  // namespace mmi

@@ -455,7 +455,7 @@ static size_t seg_header_bytes(int B, int ntile_c) { return (size_t(16) + size_t
 // L is only ever split when the unsplit grid leaves most SMs idle (the heuristic below, also applied to a forced count), so
 // the summaries' workspace is sized for kMaxSeg segments only in that case
 static int fwd_seg_cap(int B, int ntile_c) { return int64_t(B) * ntile_c * 4 <= 2 * sm_count() ? kMaxSeg : 1; }
-int64_t selscan_fwd_ws_bytes(int B, int ED) {
+int64_t selscan_fwd1_ws_bytes(int B, int ED) {
     const int gx = (ED + 31) / 32;
     return int64_t(seg_header_bytes(B, gx)) + int64_t(B) * fwd_seg_cap(B, gx) * ED * (kN + 1) * 4;
 }
@@ -513,7 +513,7 @@ static int launch_fwd_t(FwdParams p, int dtype, void *ws, cudaStream_t st) {
     return check_cuda(cudaGetLastError(), "selscan_fwd launch");
 }
 
-int selscan_fwd_launch(const FwdParams &p, int dtype, void *ws, cudaStream_t st) {
+int selscan_fwd1_launch(const FwdParams &p, int dtype, void *ws, cudaStream_t st) {
     const int cfg = (p.flags & MMI_FLAG_CFG_MASK) >> MMI_FLAG_CFG_SHIFT;
 #define MMI_FWD_DISPATCH(T)                                            \
     switch (std::is_same<T, float>::value ? cfg : 0) {                 \

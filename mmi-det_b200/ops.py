@@ -112,10 +112,10 @@ def selscan_bwd_raw(saved, chk, dout, flags=0):
 
 class _SelectiveScan(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, delta, A, Bm, Cm, D, z, flags):
-        # needs_input_grad is False under torch.no_grad() / inference even for Parameters: no checkpoints are written and
-        # nothing is saved then (tensor.requires_grad would keep both alive at inference)
-        need = any(ctx.needs_input_grad[:7])
+    def forward(ctx, x, delta, A, Bm, Cm, D, z, flags, grad_on):
+        # grad_on = torch.is_grad_enabled() at the call site (inside forward() it is always off): under torch.no_grad() /
+        # inference no checkpoints are written and nothing is saved, even though A_log / D are Parameters
+        need = grad_on and any(ctx.needs_input_grad[:7])
         out, _, chk, saved = selscan_fwd_raw(x, delta, A, Bm, Cm, D, z=z, want_chk=need, flags=flags)
         ctx.flags = flags
         ctx.has_z = z is not None
@@ -132,7 +132,7 @@ class _SelectiveScan(torch.autograd.Function):
         dx, dd, dz, dA, dB, dC, dD = selscan_bwd_raw((sx, sd, sz, sA, sB, sC, sD), chk, dout, flags=ctx.flags)
         dts = ctx.in_dtypes
         cast = lambda g, i: None if g is None else g.to(dts[i])
-        return cast(dx, 0), cast(dd, 1), cast(dA, 2), cast(dB, 3), cast(dC, 4), cast(dD, 5), (cast(dz, 6) if ctx.has_z else None), None
+        return cast(dx, 0), cast(dd, 1), cast(dA, 2), cast(dB, 3), cast(dC, 4), cast(dD, 5), (cast(dz, 6) if ctx.has_z else None), None, None
 
 
 def selective_scan(x, delta, A, B, C, D, z=None, flags: int = 0, delta_softplus: bool = False):
@@ -142,7 +142,7 @@ def selective_scan(x, delta, A, B, C, D, z=None, flags: int = 0, delta_softplus:
     the kernels (the returned gradient is then w.r.t. the pre-activation)."""
     if delta_softplus:
         flags |= _lib.FLAG_DELTA_SOFTPLUS
-    return _SelectiveScan.apply(x, delta, A, B, C, D, z, flags)
+    return _SelectiveScan.apply(x, delta, A, B, C, D, z, flags, torch.is_grad_enabled())
 
 
 class _CausalConv1dSiLU(torch.autograd.Function):
