@@ -91,6 +91,31 @@ __device__ __forceinline__ void decay8(float2 dv, float2 A2b, const float2 (&A2p
     }
 }
 
+// the same with every element multiplied by `fac` (one extra multiply in the geometric form: the factor rides on F)
+template <bool GEOM>
+__device__ __forceinline__ void decay8f(float2 dv, float2 A2b, const float2 (&A2p)[8], bool up, float2 fac, float2 (&a)[8]) {
+    if constexpr (GEOM) {
+        const float2 e = mul2(dv, A2b);
+        const float2 R = make_float2(ex2(e.x), ex2(e.y));
+        const float2 R2 = mul2(R, R), R4 = mul2(R2, R2), R8 = mul2(R4, R4);
+        const float2 F = mul2(up ? R8 : make_float2(1.f, 1.f), fac);
+        a[0] = mul2(R, F);
+        a[1] = mul2(R2, F);
+        a[2] = mul2(a[0], R2);
+        a[3] = mul2(a[1], R2);
+        a[4] = mul2(a[0], R4);
+        a[5] = mul2(a[1], R4);
+        a[6] = mul2(a[2], R4);
+        a[7] = mul2(a[3], R4);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float2 e = mul2(dv, A2p[k]);
+            a[k] = mul2(make_float2(ex2(e.x), ex2(e.y)), fac);
+        }
+    }
+}
+
 // sum of a packed pair over the two state halves (lanes l and l ^ 16): both lanes get the total
 __device__ __forceinline__ float2 xhalf_sum(float2 v) {
     const float ox = __shfl_xor_sync(0xffffffffu, v.x, 16), oy = __shfl_xor_sync(0xffffffffu, v.y, 16);

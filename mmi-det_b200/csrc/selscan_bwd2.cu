@@ -294,14 +294,16 @@ __device__ __forceinline__ void bwd2_item(const Bwd2Params &pp, const Bwd2Maps &
             ga[2 * q] = make_float2(w.x, w.y);
             ga[2 * q + 1] = make_float2(w.z, w.w);
         }
-#pragma unroll 1
-        for (int v = kNW - 1; v > wt; --v) {
-            const float4 *o = sums + (v - 1) * 8 * 32 + lane;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 G = o[q * 32], Pe = o[(4 + q) * 32];
-                ga[2 * q] = fma2(make_float2(Pe.x, Pe.y), ga[2 * q], make_float2(G.x, G.y));
-                ga[2 * q + 1] = fma2(make_float2(Pe.z, Pe.w), ga[2 * q + 1], make_float2(G.z, G.w));
+        for (int v = kNW - 1; v >= 1; --v) {  // unrolled with a warp-uniform guard: the loads of all summaries go out at once
+            if (v > wt) {
+                const float4 *o = sums + (v - 1) * 8 * 32 + lane;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 G = o[q * 32], Pe = o[(4 + q) * 32];
+                    ga[2 * q] = fma2(make_float2(Pe.x, Pe.y), ga[2 * q], make_float2(G.x, G.y));
+                    ga[2 * q + 1] = fma2(make_float2(Pe.z, Pe.w), ga[2 * q + 1], make_float2(G.z, G.w));
+                }
             }
         }
 

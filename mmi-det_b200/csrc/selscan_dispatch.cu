@@ -23,13 +23,21 @@ bool selscan_use_v2(int B, int L, int ED, int flags) {
 }
 
 int64_t selscan_bwd_ws_bytes(int B, int L, int ED) { return std::max(selscan_bwd1_ws_bytes(B, L, ED), selscan_bwd2_ws_bytes(B, L, ED)); }
-int64_t selscan_fwd_ws_bytes(int B, int ED) { return selscan_fwd1_ws_bytes(B, ED); }
+int64_t selscan_fwd_ws_bytes(int B, int ED) { return std::max(selscan_fwd1_ws_bytes(B, ED), selscan_fwd2_ws_bytes(B, 0, ED)); }
 
 int selscan_bwd_launch(BwdParams p, int dtype, void *ws, cudaStream_t st) {
     if (selscan_use_v2(p.B, p.L, p.ED, p.flags)) return selscan_bwd2_launch(p, dtype, ws, st);
     return selscan_bwd1_launch(p, dtype, ws, st);
 }
 
-int selscan_fwd_launch(const FwdParams &p, int dtype, void *ws, cudaStream_t st) { return selscan_fwd1_launch(p, dtype, ws, st); }
+// The forward stays on the first generation unless forced: its two independent 4-warp CTAs per SM hide each other's
+// barrier stalls, which the 8-warp persistent CTA cannot (measured at the bench shape, profiles/r02_scan_generations.txt:
+// 0.372 ms vs 0.426 ms with checkpoints); the backward, whose 255-register / tensor-memory footprint allows one CTA per SM
+// either way, gains from the second generation (1.224 -> 1.01 ms).
+int selscan_fwd_launch(const FwdParams &p, int dtype, void *ws, cudaStream_t st) {
+    const int cfg = (p.flags & MMI_FLAG_CFG_MASK) >> MMI_FLAG_CFG_SHIFT;
+    if (ws && cfg == 8) return selscan_fwd2_launch(p, dtype, ws, st);
+    return selscan_fwd1_launch(p, dtype, ws, st);
+}
 
 }  // namespace mmi

@@ -173,3 +173,44 @@ def test_v2_kernels_stay_inside_their_outputs(shape, dtype):
         assert bool((buf[:GUARD] == 7).all()) and bool((buf[GUARD + n:] == 7).all()), f"guard band of arena {i} overwritten"
     for t in (out, dx, dd, dz, dA, dD, dB, dC):
         assert bool(torch.isfinite(t.float()).all())
+
+
+@pytest.mark.parametrize("nseg", [0, 1, 3])
+@pytest.mark.parametrize("random_A", [False, True])
+def test_v2_forward_matches_first_generation(nseg, random_A):
+    """outputs, final state hT and checkpoints of the second-generation forward == the first generation's, with a non-zero
+    h0, a ragged tail and chained segments; and h0 -> hT chaining over a cut equals one call."""
+    from mmidet_b200 import ops
+    B, L, ED = 3, 1100, 136
+    inp = scan_inputs(B, L, ED, seed=nseg + 40, random_A=random_A)
+    a = {k: _t(v) for k, v in inp.items()}
+    h0 = torch.randn(B, ED, 16, device="cuda")
+    run = lambda fl, **kw: ops.selscan_fwd_raw(a["x"], a["delta"], a["A"], a["Bm"], a["Cm"], a["D"], z=a["z"], want_state=True,
+                                               want_chk=True, flags=fl, **kw)
+    o1, hT1, chk1, _ = run(9 << 4, h0=h0)
+    o2, hT2, chk2, _ = run(V2 | (nseg << 8), h0=h0)
+    for u, v in ((o1, o2), (hT1, hT2), (chk1, chk2)):
+        assert relerr(v.cpu().numpy(), u.cpu().numpy()) <= 2e-5
+    ref_out, ref_h = O.selective_scan_fwd(inp["x"], inp["delta"], inp["A"], inp["Bm"], inp["Cm"], inp["D"], z=inp["z"],
+                                          h0=h0.cpu().numpy(), dtype=np.float64, return_state=True)
+    assert relerr(o2.cpu().numpy(), ref_out) <= 1e-4 and relerr(hT2.cpu().numpy(), ref_h) <= 1e-4
+    cut = 517
+    sl = lambda t, s: t[:, s].contiguous()
+    first = ops.selscan_fwd_raw(sl(a["x"], slice(0, cut)), sl(a["delta"], slice(0, cut)), a["A"], sl(a["Bm"], slice(0, cut)),
+                                sl(a["Cm"], slice(0, cut)), a["D"], z=sl(a["z"], slice(0, cut)), h0=h0, want_state=True, flags=V2)
+    second = ops.selscan_fwd_raw(sl(a["x"], slice(cut, L)), sl(a["delta"], slice(cut, L)), a["A"], sl(a["Bm"], slice(cut, L)),
+                                 sl(a["Cm"], slice(cut, L)), a["D"], z=sl(a["z"], slice(cut, L)), h0=first[1], want_state=True,
+                                 flags=V2)
+    assert relerr(torch.cat([first[0], second[0]], 1).cpu().numpy(), o2.cpu().numpy()) <= 1e-5
+    assert relerr(second[1].cpu().numpy(), hT2.cpu().numpy()) <= 1e-5
+
+
+def test_v2_strided_views():
+    """x / z passed as chunk() views of one GEMM output (row pitch 2 * ED), as MambaBlock.forward produces them."""
+    from mmidet_b200 import ops
+    B, L, ED = 2, 300, 64
+    inp = scan_inputs(B, L, ED, seed=5, random_A=True)
+    xz = torch.cat([_t(inp["x"]), _t(inp["z"])], dim=-1)
+    xv, zv = xz.chunk(2, dim=-1)
+    out = ops.selscan_fwd_raw(xv, _t(inp["delta"]), _t(inp["A"]), _t(inp["Bm"]), _t(inp["Cm"]), _t(inp["D"]), z=zv, flags=V2)[0]
+    assert relerr(out.cpu().numpy(), _oracle(inp)["out"]) <= 1e-4
