@@ -96,7 +96,7 @@ def detector_cfg(size: str = "l", nc: int = 6, yaml_rel: str = FUSION_YAML) -> d
 
 
 def build_detector(size: str = "l", arm: str = "ours", nc: int = 6, seed: int = 0, n_layer: int = 1, device="cuda",
-                   state_dict=None):
+                   state_dict=None, channels_last: bool = False):
     """Model(cfg) of the unmodified reference with the YAML name `GPT` bound to
         arm="ours"     mmidet_b200.mamba.MambaFusion (fused sm_100a kernels)
         arm="pytorch"  the same MambaFusion wrapper on the reference's models.mamba.ResidualBlock (pure PyTorch pscan)
@@ -121,7 +121,12 @@ def build_detector(size: str = "l", arm: str = "ours", nc: int = 6, seed: int = 
         Y.GPT = old
     if state_dict is not None:
         model.load_state_dict(state_dict, strict=True)
-    return model.to(device)
+    model = model.to(device)
+    if channels_last:
+        # stock PyTorch switch (no reference edit): cuDNN convolutions and batch norms run NHWC -- their native layout on
+        # tensor cores -- and the feature maps reach the fusion blocks as ready-made token rows
+        model = model.to(memory_format=torch.channels_last)
+    return model
 
 
 def scale_hyp(model, nc: int, imgsz: int):
@@ -170,6 +175,17 @@ def synthetic_batch(B: int, imgsz: int, nc: int = 6, boxes_per_image: int = 8, s
     t[:, 2:4] = torch.rand(n, 2, generator=g) * 0.8 + 0.1
     t[:, 4:6] = torch.rand(n, 2, generator=g) * 0.25 + 0.05
     return imgs.to(device), t.to(device)
+
+
+def prepare_inference(model, dtype=torch.float16, fuse: bool = True, channels_last: bool = False):
+    """What the reference's loader does before detect_twostream.py's loop: Conv + BatchNorm folding (models/experimental.py:119
+    `.fuse().eval()`, the reference's own Model.fuse) and the half() of detect_twostream.py:45."""
+    model = model.eval()
+    if fuse:
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            model = model.fuse()  # (before any layout change: fuse_conv_and_bn views the weights as NCHW-contiguous)
+    model = model.to(dtype)
+    return model.to(memory_format=torch.channels_last) if channels_last else model
 
 
 def prep_inputs(imgs_u8: torch.Tensor, dtype=torch.float32):

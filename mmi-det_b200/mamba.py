@@ -186,6 +186,11 @@ class Mamba(nn.Module):
         return x, caches
 
 
+def _is_channels_last(t):
+    return t.dim() == 4 and t.stride(1) == 1 and t.stride(3) == t.shape[1] and t.stride(2) == t.shape[3] * t.shape[1] \
+        and t.stride(0) == t.shape[2] * t.shape[3] * t.shape[1]
+
+
 class MambaFusion(nn.Module):
     """Cross-modal fusion with the `GPT` contract (models/common.py:1270-1370).
 
@@ -217,6 +222,14 @@ class MambaFusion(nn.Module):
             return out[:, :, 0].contiguous(), out[:, :, 1].contiguous()
         if ir.dtype != rgb.dtype:
             ir = ir.to(rgb.dtype)
+        if rgb.is_cuda and C > 1 and _is_channels_last(rgb) and _is_channels_last(ir):
+            # a channels_last backbone hands over maps that already ARE token rows (B, HW, C): the gather is the concatenation
+            # of two contiguous blocks and the way back is two views of the token tensor -- no transpose in either direction
+            tok = torch.cat([rgb.permute(0, 2, 3, 1).reshape(B, H * W, C), ir.permute(0, 2, 3, 1).reshape(B, H * W, C)], dim=1)
+            for layer in self.layers:
+                tok = layer(tok)
+            out = tok.view(B, 2, H, W, C)
+            return out[:, 0].permute(0, 3, 1, 2), out[:, 1].permute(0, 3, 1, 2)
         tok = ops.tokens_gather(rgb, ir)  # (B, 2HW, C), VIS tokens then IR tokens: one tiled transpose (raises off-GPU)
         for layer in self.layers:
             tok = layer(tok)

@@ -74,7 +74,7 @@ def mode_train(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-    model = H.build_detector(args.size, args.arm, seed=0).train()
+    model = H.build_detector(args.size, args.arm, seed=0, channels_last=args.channels_last).train()
     hyp = H.scale_hyp(model, 6, args.imgsz)
     ref = H.import_reference()
     compute_loss = ref.loss.ComputeLoss(model)
@@ -114,7 +114,8 @@ def mode_train(args):
         ms = float(t[0])
         print(json.dumps({"mode": "train", "arm": args.arm, "n_gpus": world,
                           "config": f"two-stream YOLOv5{args.size} training step, {args.imgsz}x{args.imgsz} synthetic pairs, batch "
-                                    f"{args.batch}/GPU, autocast {args.autocast}, SGD, DDP bucket {args.bucket_mb} MB",
+                                    f"{args.batch}/GPU, autocast {args.autocast}, SGD, DDP bucket {args.bucket_mb} MB, "
+                                    f"{'channels_last' if args.channels_last else 'NCHW'} backbone",
                           "pairs_per_s": round(world * args.batch / (ms * 1e-3), 2), "ms_per_step": round(ms, 3),
                           "params": nparam, "allreduce_bytes_per_step": nparam * 4 if world > 1 else 0,
                           "loss": float(loss), "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 2)}), flush=True)
@@ -127,11 +128,11 @@ def mode_infer(args):
     from mmidet_b200 import harness as H
     from mmidet_b200 import postprocess
     ref = H.import_reference()
-    model = H.build_detector(args.size, args.arm, seed=0).eval()
+    dt = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[args.dtype]
+    model = H.prepare_inference(H.build_detector(args.size, args.arm, seed=0), dt, fuse=not args.no_fuse,
+                                channels_last=args.channels_last)
     if args.arm == "ours":
         postprocess.install_detect(ref.yolo_test)
-    dt = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[args.dtype]
-    model = model.to(dt)
     imgs, _ = H.synthetic_batch(args.batch, args.imgsz, seed=7)
 
     def once():
@@ -148,7 +149,8 @@ def mode_infer(args):
     p50, p99 = ts[len(ts) // 2], ts[min(len(ts) - 1, int(len(ts) * 0.99))]
     print(json.dumps({"mode": "infer", "arm": args.arm,
                       "config": f"two-stream YOLOv5{args.size} inference (input prep + forward + NMS, detect_twostream.py:74-94), "
-                                f"{args.imgsz}x{args.imgsz}, batch {args.batch}, {args.dtype}",
+                                f"{args.imgsz}x{args.imgsz}, batch {args.batch}, {args.dtype}, Conv+BN {'fused' if not args.no_fuse else 'unfused'}, "
+                                f"{'channels_last' if args.channels_last else 'NCHW'} backbone",
                       "pairs_per_s": round(args.batch / (p50 * 1e-3), 2), "ms_p50": round(p50, 3), "ms_p99": round(p99, 3),
                       "detections": int(sum(d.shape[0] for d in det)),
                       "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 2)}), flush=True)
@@ -167,6 +169,8 @@ def main():
     ap.add_argument("--dtype", default="fp16")
     ap.add_argument("--conf", type=float, default=0.25)
     ap.add_argument("--bucket-mb", dest="bucket_mb", type=int, default=8)
+    ap.add_argument("--channels-last", dest="channels_last", action="store_true")
+    ap.add_argument("--no-fuse", dest="no_fuse", action="store_true")
     args = ap.parse_args()
     d = {"logits": ("s", 640, 1), "train": ("l", 640, 16), "infer": ("x", 1280, 32)}[args.mode]
     args.size = args.size or d[0]

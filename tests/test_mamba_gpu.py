@@ -309,3 +309,24 @@ def test_inference_skips_checkpoints(monkeypatch):
     y2 = ops.selective_scan(x, delta, A, Bm, Cm, D)
     assert y2.grad_fn is not None and seen == [False, True]
     assert torch.equal(y, y2.detach())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fusion_accepts_channels_last_maps(dtype):
+    """maps from a channels_last backbone take the no-transpose route (concatenate token rows, return views): same values
+    and gradients as the NCHW route."""
+    from mmidet_b200.mamba import MambaFusion
+    torch.manual_seed(0)
+    fus = MambaFusion(32).cuda().to(dtype)
+    a, b = torch.randn(2, 32, 9, 7, device="cuda", dtype=dtype), torch.randn(2, 32, 9, 7, device="cuda", dtype=dtype)
+    x1 = [a.clone().requires_grad_(True), b.clone().requires_grad_(True)]
+    x2 = [a.clone().contiguous(memory_format=torch.channels_last).requires_grad_(True),
+          b.clone().contiguous(memory_format=torch.channels_last).requires_grad_(True)]
+    o1, o2 = fus(x1), fus(x2)
+    assert o2[0].stride(1) == 1 and o2[0].shape == a.shape  # channel-innermost views of the token tensor (no copy)
+    g = torch.randn_like(a)
+    g1 = torch.autograd.grad([o1[0], o1[1]], x1, [g, g])
+    g2 = torch.autograd.grad([o2[0], o2[1]], x2, [g, g])
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    for u, v in zip(o1 + g1, o2 + g2):
+        assert relerr(v.float().cpu().numpy(), u.float().cpu().numpy()) <= tol
