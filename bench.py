@@ -17,6 +17,13 @@ need the reference detector, which does not travel to the GPU box; they are pari
   roofline  dominant kernel (the backward scan): algorithmic bytes / its event-timed duration vs measured HBM peak.
   cpu_baseline / --impl reference: the CPU oracle (oracle/, C + OpenMP port of the reference algorithm) on a
             bounded sample of the same workload, all host cores.
+  parity_relerr   batch entry 0 of the timed step's outputs against the fp64 oracle (the checker, after the timed region).
+  general_A / bf16   the same step with a trained (non-geometric) A, and with bf16 I/O: what a training run sees after the
+            first optimizer step / under autocast (secondary legs, a few steps each).
+  train     BASELINE configs[3]: the data-parallel training step of the UNMODIFIED reference detector (two-stream
+            YOLOv5l, 16 synthetic pairs per GPU, bf16 autocast, ComputeLoss, SGD) with the CUDA fusion path plugged in,
+            DDP gradient all-reduce over NCCL overlapped with the backward (8 MB buckets); `exposed_allreduce_ms` is the
+            step time minus the same step under no_sync().  Needs the staged reference (baseline/_ref).
 Only this file's cpu legs and tests/ touch oracle/; the product path is the CUDA library and fails loudly
 without it."""
 from __future__ import annotations
@@ -169,6 +176,70 @@ def workload_config(**extra):
     return c
 
 
+def parity_check(t, out, grads, b=0):
+    """batch entry b of one step's outputs vs the fp64 oracle (checker only; after the timed region)."""
+    import numpy as np
+    from oracle import oracle as O
+    f64 = lambda v: v[b:b + 1].detach().double().cpu().numpy()
+    A, D = t["A"].double().cpu().numpy(), t["D"].double().cpu().numpy()
+    a = {k: f64(t[k]) for k in ("x", "delta", "z", "Bm", "Cm", "dout")}
+    ref = O.selective_scan_bwd(a["x"], a["delta"], A, a["Bm"], a["Cm"], D, a["dout"], z=a["z"], dtype=np.float64)
+    ref["out"] = O.selective_scan_fwd(a["x"], a["delta"], A, a["Bm"], a["Cm"], D, z=a["z"], dtype=np.float64)
+    got = dict(out=out, dx=grads[0], ddelta=grads[1], dz=grads[2], dB=grads[4], dC=grads[5])
+    rel = lambda u, v: float(np.max(np.abs(u - v)) / max(np.max(np.abs(v)), 1e-30))
+    return {k: float(f"{rel(f64(v), ref[k]):.3g}") for k, v in got.items()}
+
+
+def detector_train_leg(rank, world, local_rank, dist, steps=5, warmup=3):
+    """BASELINE configs[3] on the unmodified reference detector with the CUDA fusion path (see module docstring)."""
+    import contextlib
+    import torch
+    from mmidet_b200 import harness as H
+    ref = H.import_reference()
+    B, imgsz = 16, 640
+    model = H.build_detector("l", "ours", seed=0, channels_last=True).train()
+    hyp = H.scale_hyp(model, 6, imgsz)
+    compute_loss = ref.loss.ComputeLoss(model)
+    opt = H.make_optimizer(model, hyp, B * world)
+    nparam = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    net = model
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        # 8 MB buckets: the all-reduce of the early (head) buckets hides under the rest of the backward
+        net = DDP(model, device_ids=[local_rank], output_device=local_rank, bucket_cap_mb=8, gradient_as_bucket_view=True,
+                  broadcast_buffers=False)
+    imgs, targets = H.synthetic_batch(B, imgsz, seed=100 + rank)
+
+    def run(n, sync=True):
+        ctx = net.no_sync() if (world > 1 and not sync) else contextlib.nullcontext()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        with ctx:
+            for _ in range(n):
+                loss = H.train_step(net, compute_loss, opt, imgs, targets, autocast_dtype=torch.bfloat16, world_size=world)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / n], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(loss)
+
+    run(warmup)
+    ms, loss = run(steps)
+    leg = {"config": "two-stream YOLOv5l (unmodified reference Model / ComputeLoss, fusion = MambaFusion on the sm_100a kernels), "
+                     "640x640 synthetic pairs, 16 / GPU, bf16 autocast, SGD, channels_last backbone",
+           "pairs_per_s": round(world * B / (ms * 1e-3), 2), "ms_per_step": round(ms, 3), "n_gpus": world, "steps": steps,
+           "params": nparam, "allreduce_bytes_per_step": nparam * 4 if world > 1 else 0, "loss": round(loss, 5)}
+    if world > 1:
+        ms_nosync, _ = run(steps, sync=False)
+        leg["ms_per_step_no_allreduce"] = round(ms_nosync, 3)
+        leg["exposed_allreduce_ms"] = round(ms - ms_nosync, 3)
+    return leg
+
+
 # ------------------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
     import torch
@@ -246,6 +317,35 @@ def run_ours(args, rank, world, local_rank):
     t_step = t_f + t_b
     checksum = float(out.float().abs().mean()) + float(grads[0].float().abs().mean())
 
+    # ---- secondary legs (untimed by the contract; a few steps each) -------------------------------------------------
+    parity = None
+    if rank == 0 and not args.no_cpu:
+        try:
+            parity = parity_check(dict(x=x, delta=delta, z=z, Bm=Bm, Cm=Cm, dout=dout, A=A, D=D), out, grads)
+        except Exception as e:  # the oracle is a checker; its absence must not hide the GPU number
+            parity = {"error": repr(e)}
+
+    def quick(xx, dd, zz, BB, CC, gg, AA, n=5):
+        def one():
+            flush.zero_()
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            e[0].record()
+            o, _, ck, sv = ops.selscan_fwd_raw(xx, dd, AA, BB, CC, D, z=zz, want_chk=True)
+            ops.selscan_bwd_raw(sv, ck, gg)
+            e[1].record()
+            torch.cuda.synchronize()
+            return e[0].elapsed_time(e[1])
+        for _ in range(3):
+            one()
+        ts = sorted(one() for _ in range(n))
+        return ts[len(ts) // 2]
+
+    A_tr = -torch.exp(torch.randn(ED, N, device=dev, generator=g) * 0.5 + 0.3)  # a trained A_log: no geometric rows
+    t_gen = quick(x, delta, z, Bm, Cm, dout, A_tr)
+    hb = lambda t: t.to(torch.bfloat16)
+    t_bf = quick(hb(x), hb(delta), hb(z), hb(Bm), hb(Cm), hb(dout), A)
+    fb16, bb16 = alg_bytes(B, L, ED, N, 2)
+
     # ---- end-to-end through the host-buffer C ABI (pinned host memory, H2D + kernels + D2H) -------------------
     e2e = None
     e2e_steps = max(2, min(args.steps, 5))
@@ -277,10 +377,20 @@ def run_ours(args, rank, world, local_rank):
         e2e = (t_e2e, h2d, d2h, e2e_check)
 
     # ---- max over ranks -------------------------------------------------------------------------------------
-    times = torch.tensor([t_step, t_f, t_b, e2e[0] * 1e3 if e2e else 0.0], device=dev, dtype=torch.float64)
+    times = torch.tensor([t_step, t_f, t_b, e2e[0] * 1e3 if e2e else 0.0, t_gen, t_bf], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_step, t_f, t_b, t_e2e_ms = [float(v) for v in times]
+    t_step, t_f, t_b, t_e2e_ms, t_gen, t_bf = [float(v) for v in times]
+
+    train_leg = None
+    if not args.no_train:
+        hold.clear()
+        del out, grads
+        torch.cuda.empty_cache()
+        try:
+            train_leg = detector_train_leg(rank, world, local_rank, dist)
+        except Exception as e:  # e.g. the reference checkout was not staged: the scan numbers still stand
+            train_leg = {"error": repr(e)[:300]}
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -288,7 +398,7 @@ def run_ours(args, rank, world, local_rank):
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("selscan_bwd_kernel", {}).get("dram_bytes_per_launch")
+                traffic = json.load(open(tp)).get("selscan_bwd2_kernel", {}).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
         val = world * (fb + bb) / (t_step * 1e-3) / 1e9
@@ -296,7 +406,7 @@ def run_ours(args, rank, world, local_rank):
                 "warmup": max(args.warmup, 3), "ms_per_step": round(t_step, 4), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(),
                 "frac_of_hbm_peak": round(val / world / peak, 4),
-                "roofline": {"bound": "hbm", "kernel": "selscan_bwd_kernel<float> (+ partial-reduction kernel)",
+                "roofline": {"bound": "hbm", "kernel": "selscan_bwd2_kernel<float, true> (+ partial-reduction kernel)",
                              "achieved": round(bb / (t_b * 1e-3) / 1e9, 2), "peak": peak, "unit": "GB/s",
                              "frac": round(bb / (t_b * 1e-3) / 1e9 / peak, 4), "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": bb, "ms_per_launch": round(t_b, 4)},
@@ -304,6 +414,13 @@ def run_ours(args, rank, world, local_rank):
                                  "achieved": round(fb / (t_f * 1e-3) / 1e9, 2), "peak": peak, "unit": "GB/s",
                                  "frac": round(fb / (t_f * 1e-3) / 1e9 / peak, 4), "algorithmic_bytes_per_launch": fb,
                                  "ms_per_launch": round(t_f, 4)},
+                "general_A": {"what": "same step, trained (non-geometric) A: 16 exponentials per step instead of 1",
+                              "value": round(world * (fb + bb) / (t_gen * 1e-3) / 1e9, 2), "unit": UNIT, "ms_per_step": round(t_gen, 4),
+                              "frac_of_hbm_peak": round((fb + bb) / (t_gen * 1e-3) / 1e9 / peak, 4)},
+                "roofline_bf16": {"what": "same step, bf16 I/O (fp32 state): half the algorithmic bytes, same arithmetic",
+                                  "achieved": round((fb16 + bb16) / (t_bf * 1e-3) / 1e9, 2), "peak": peak, "unit": "GB/s",
+                                  "frac": round((fb16 + bb16) / (t_bf * 1e-3) / 1e9 / peak, 4), "ms_per_step": round(t_bf, 4)},
+                "parity_relerr": parity, "train": train_leg,
                 "clocks": clocks, "gpu_launches": launches, "checksum": round(checksum, 6)}
         if e2e:
             line["e2e"] = {"value": round(world * (fb + bb) / (t_e2e_ms * 1e-3) / 1e9, 3), "unit": UNIT,
@@ -329,6 +446,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the detector DDP training leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -342,6 +460,7 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"), __file__,
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
         cmd += ["--no-e2e"] if args.no_e2e else []
+        cmd += ["--no-train"] if args.no_train else []
         sys.exit(subprocess.call(cmd))
     run_ours(args, rank, world, local_rank)
 

@@ -44,8 +44,9 @@ def main():
             ts.append(e0.elapsed_time(e1))
         return sorted(ts)[len(ts) // 2]
 
-    lines = [f"| dtype | B | L | d_inner | fwd ms | fwd GB/s | bwd ms | bwd GB/s | fwd+bwd GB/s | % of {peak:.0f} GB/s |", "|---|---|---|---|---|---|---|---|---|---|"]
-    for dname, dt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+    lines = [f"| dtype | A | B | L | d_inner | fwd ms | fwd GB/s | bwd ms | bwd GB/s | fwd+bwd GB/s | % of {peak:.0f} GB/s |", "|---|---|---|---|---|---|---|---|---|---|---|"]
+    for dname, dt, aname in (("fp32", torch.float32, "S4D-real"), ("fp32", torch.float32, "trained"),
+                             ("bf16", torch.bfloat16, "S4D-real"), ("bf16", torch.bfloat16, "trained")):
         for L in (400, 1600, 6400, 25600):
             for ED in (256, 512, 1024):
                 B = a.B if L * ED <= 6400 * 1024 else max(2, a.B // 4)
@@ -57,17 +58,20 @@ def main():
                 dout = torch.randn(B, L, ED, device=dev).to(dt)
                 D = torch.ones(ED, device=dev)
                 A = -torch.arange(1, N + 1, device=dev, dtype=torch.float32).repeat(ED, 1)
+                if aname == "trained":  # A_log after training: no geometric rows, 16 exponentials per step
+                    A = -torch.exp(torch.randn(ED, N, device=dev) * 0.5 + 0.3)
                 fb, bb = alg_bytes(B, L, ED, N, x.element_size())
                 tf = timeit(lambda: ops.selscan_fwd_raw(x, delta, A, Bm, Cm, D, z=z, want_chk=True))
                 _, _, chk, saved = ops.selscan_fwd_raw(x, delta, A, Bm, Cm, D, z=z, want_chk=True)
                 tb = timeit(lambda: ops.selscan_bwd_raw(saved, chk, dout))
                 tot = (fb + bb) / (tf + tb) / 1e6
-                lines.append(f"| {dname} | {B} | {L} | {ED} | {tf:.3f} | {fb/tf/1e6:.0f} | {tb:.3f} | {bb/tb/1e6:.0f} | {tot:.0f} | {100*tot/peak:.1f} |")
+                lines.append(f"| {dname} | {aname} | {B} | {L} | {ED} | {tf:.3f} | {fb/tf/1e6:.0f} | {tb:.3f} | {bb/tb/1e6:.0f} | {tot:.0f} | {100*tot/peak:.1f} |")
                 print(lines[-1], flush=True)
                 del x, delta, z, Bm, Cm, dout, chk, saved
     if a.out:
         with open(a.out, "w") as f:
-            f.write("# Fused selective scan sweep (BASELINE configs[2]), one B200, S4D-real A, gate fused, checkpoints written\n\n")
+            f.write("# Fused selective scan sweep (BASELINE configs[2]), one B200, both A paths (S4D-real init = geometric rows, one "
+                    "exponential per step; trained = general rows, 16 per step), gate fused, checkpoints written\n\n")
             f.write("\n".join(lines) + "\n")
 
 

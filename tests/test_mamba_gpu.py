@@ -329,4 +329,4 @@ def test_fusion_accepts_channels_last_maps(dtype):
     g2 = torch.autograd.grad([o2[0], o2[1]], x2, [g, g])
     tol = 1e-5 if dtype == torch.float32 else 2e-2
     for u, v in zip(o1 + g1, o2 + g2):
-        assert relerr(v.float().cpu().numpy(), u.float().cpu().numpy()) <= tol
+        assert relerr(v.detach().float().cpu().numpy(), u.detach().float().cpu().numpy()) <= tol
