@@ -190,7 +190,7 @@ def parity_check(t, out, grads, b=0):
     return {k: float(f"{rel(f64(v), ref[k]):.3g}") for k, v in got.items()}
 
 
-def detector_train_leg(rank, world, local_rank, dist, steps=5, warmup=3):
+def detector_train_leg(rank, world, local_rank, dist, steps=8, warmup=5):
     """BASELINE configs[3] on the unmodified reference detector with the CUDA fusion path (see module docstring)."""
     import contextlib
     import torch
@@ -236,7 +236,7 @@ def detector_train_leg(rank, world, local_rank, dist, steps=5, warmup=3):
     if world > 1:
         ms_nosync, _ = run(steps, sync=False)
         leg["ms_per_step_no_allreduce"] = round(ms_nosync, 3)
-        leg["exposed_allreduce_ms"] = round(ms - ms_nosync, 3)
+        leg["exposed_allreduce_ms"] = round(max(0.0, ms - ms_nosync), 3)  # (step-to-step noise is about +-2 ms)
     return leg
 
 

@@ -29,45 +29,87 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+HASH_PATH = SO_PATH + ".srchash"
+
+
+def _dep_files():
+    return sources() + sorted(glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) +
+                              glob.glob(os.path.join(_ROOT, "include", "*.h")))
+
+
+def source_hash() -> str:
+    """sha256 over every source / header the library is built from (names + contents) and the compiler flags."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for f in _dep_files():
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not os.path.exists(SO_PATH):
+    """Stale = the sources' content hash differs from the one recorded next to the library at build time.  (File times are
+    useless here: the repository travels to the GPU box as a snapshot whose mtimes are in copy order.)"""
+    if not os.path.exists(SO_PATH) or not os.path.exists(HASH_PATH):
         return True
-    t = os.path.getmtime(SO_PATH)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) + \
-        glob.glob(os.path.join(_ROOT, "include", "*.h"))
-    return any(os.path.getmtime(f) > t for f in deps)
+    try:
+        return open(HASH_PATH).read().strip() != source_hash()
+    except OSError:
+        return True
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """nvcc -gencode arch=compute_100a,code=sm_100a ... -> mmi-det_b200/libmmidet_b200.so (in-tree).
-    Every csrc/*.cu is compiled to an object in parallel (the two scan kernels dominate), then linked."""
-    if not force and not needs_build():
-        return SO_PATH
+    Every csrc/*.cu is compiled to an object in parallel (the scan kernels dominate), then linked.  Serialised across
+    processes by a file lock and published atomically, so that the ranks of a torchrun job can all call load() at once."""
+    import fcntl
+    lock_path = SO_PATH + ".lock"
+    with open(lock_path, "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return SO_PATH  # another process built it while this one waited for the lock
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> str:
     from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
     objdir = os.path.join(_DIR, "build")
     os.makedirs(objdir, exist_ok=True)
-    hdrs = glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(_ROOT, "include", "*.h"))
-    newest_hdr = max(os.path.getmtime(f) for f in hdrs)
+    hdrs = [f for f in _dep_files() if not f.endswith(".cu")]
+    import hashlib
+    hdr_hash = hashlib.sha256(b"".join(open(f, "rb").read() for f in hdrs) + " ".join(NVCC_FLAGS).encode()).hexdigest()
     log = []
 
     def compile_one(src):
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
-        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), newest_hdr):
+        tag = obj + ".srchash"
+        want = hashlib.sha256(open(src, "rb").read() + hdr_hash.encode()).hexdigest()
+        if not force and os.path.exists(obj) and os.path.exists(tag) and open(tag).read().strip() == want:
             return obj
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n" + r.stdout + r.stderr)
+        with open(tag, "w") as f:
+            f.write(want)
         log.append(r.stderr)
         return obj
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
         objs = list(pool.map(compile_one, sources()))
-    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO_PATH] + objs,
+    tmp = SO_PATH + f".tmp{os.getpid()}"
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs,
                        capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
+    os.replace(tmp, SO_PATH)  # atomic: a concurrent dlopen sees the old or the new file, never a partial one
+    with open(HASH_PATH, "w") as f:
+        f.write(source_hash())
     if verbose:
         print("".join(log))
     return SO_PATH
