@@ -115,8 +115,9 @@ class MambaBlock(nn.Module):
             delta_pre = dtp(delta)
         return self.selective_scan(x, delta_pre, A, B, C, self.D.float(), z=z, delta_softplus=True)
 
-    def forward(self, x):
-        L = x.shape[1]
+    def forward(self, x, residual=None):
+        """models/mamba.py:165-189.  `residual` (same shape and dtype as the output) is added in out_proj's GEMM epilogue
+        (addmm, beta = 1): ResidualBlock's `mixer(norm(x)) + x` (models/mamba.py:101) without a separate pass over (B, L, D)."""
         xz = self.in_proj(x)
         xs, z = xz.chunk(2, dim=-1)  # views of one GEMM output: passed to the kernel by row pitch, never copied
         if self.config.d_conv > 4 or self.conv1d.groups != self.conv1d.in_channels:
@@ -125,7 +126,12 @@ class MambaBlock(nn.Module):
         # depthwise causal conv + SiLU on the channels-last tokens (no transposes, models/mamba.py:176-180)
         xs = ops.causal_conv1d_silu(xs, self.conv1d.weight, self.conv1d.bias)
         y = self.ssm(xs, z=z)  # = ssm(x) * silu(z): the gate of models/mamba.py:184-186 is fused into the scan
-        return self.out_proj(y.to(xz.dtype))
+        y = y.to(xz.dtype)
+        op = self.out_proj
+        if residual is not None and op.bias is None and residual.dtype == y.dtype and not torch.is_autocast_enabled():
+            return torch.addmm(residual.reshape(-1, residual.shape[-1]), y.reshape(-1, y.shape[-1]), op.weight.t()).view(residual.shape)
+        out = op(y)
+        return out if residual is None else out + residual
 
     # -- single-token recurrent inference (models/mamba.py:289-353): same cache contract (h (B, ED, N) or None, inputs
     #    (B, ED, d_conv-1)); the conv window and the one-step scan run on the same kernels as forward() (L = d_conv / L = 1,
@@ -162,7 +168,7 @@ class ResidualBlock(nn.Module):
         self.norm = RMSNorm(config.d_model)
 
     def forward(self, x):
-        return self.mixer(self.norm(x)) + x
+        return self.mixer(self.norm(x), residual=x)  # + x folded into out_proj's epilogue where dtypes allow
 
     def step(self, x, cache):
         out, cache = self.mixer.step(self.norm(x), cache)
