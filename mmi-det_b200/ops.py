@@ -239,7 +239,7 @@ def rmsnorm(x, weight, eps: float = 1e-5):
     if x.dtype == torch.float32 and torch.is_autocast_enabled():
         # autocast runs norms in fp32 and casts their output for the 16-bit GEMM that follows: emit that dtype directly
         # (one rounding either way) and take the 16-bit gradient as it comes -- two cast passes over (B, L, C) saved
-        ac = torch.get_autocast_gpu_dtype()
+        ac = torch.get_autocast_dtype("cuda")
         if ac in (torch.bfloat16, torch.float16):
             out_dtype = ac
     return _RMSNorm.apply(x, weight, eps, out_dtype)

@@ -1,0 +1,2 @@
+timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -6
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
