@@ -13,6 +13,7 @@ the reference's own drivers do inline:
                                       A_log / D land in no group, SURVEY App. B -- kept, it is the reference's behaviour)
     train_step                        train.py:783-804 (autocast forward, ComputeLoss, backward, optimizer step)
     infer                             detect_twostream.py:88-94 (model forward + non_max_suppression timing window)
+    load_checkpoint                   models/experimental.py:113-134 (attempt_load) for the checkpoints train.py:882-894 writes
     quiet()                           the per-step print()/sync points of utils/loss.py:162-182 and
                                       models/yolo_test.py:253,269: formatting a CUDA tensor for print is a
                                       device synchronisation; the module-global name `print` is shadowed by a no-op in those
@@ -186,6 +187,31 @@ def prepare_inference(model, dtype=torch.float16, fuse: bool = True, channels_la
             model = model.fuse()  # (before any layout change: fuse_conv_and_bn views the weights as NCHW-contiguous)
     model = model.to(dtype)
     return model.to(memory_format=torch.channels_last) if channels_last else model
+
+
+def load_checkpoint(path: str, map_location="cpu", fuse: bool = True, install_path: bool = True):
+    """models/experimental.py:113-134 (`attempt_load`, single model) and train.py:882-894's format: a pickled dict whose
+    'ema' or 'model' entry is the whole module.  The reference's own call breaks on torch >= 2.6 (`weights_only` defaults to
+    True) and would try to download a missing file; this does the same steps without either: unpickle with the
+    reference checkout importable, take the EMA model if present, `.float()`, the reference's `fuse()`, `.eval()`, the
+    compatibility fix-ups.  install_path=True additionally binds the CUDA path onto the reference classes the checkpoint's
+    modules are instances of (mamba.install: scan / pscan / FFM), so the loaded detector runs on the kernels as is."""
+    ref = import_reference()
+    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+    model = ckpt["ema" if ckpt.get("ema") else "model"].float()
+    if fuse:
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            model = model.fuse()
+    model = model.eval()
+    for m in model.modules():
+        if type(m) in (nn.Hardswish, nn.LeakyReLU, nn.ReLU, nn.ReLU6, nn.SiLU):
+            m.inplace = True
+        elif type(m) is ref.common.Conv:
+            m._non_persistent_buffers_set = set()
+    if install_path:
+        from . import mamba as ours
+        ours.install(scan=True, pscan=True, ffm=True, fusion=False)
+    return model
 
 
 def prep_inputs(imgs_u8: torch.Tensor, dtype=torch.float32):

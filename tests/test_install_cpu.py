@@ -87,3 +87,27 @@ def test_staged_reference_is_unmodified():
         assert hashlib.sha256(data).hexdigest() == digest, rel
         if os.path.isdir(src):
             assert data == open(os.path.join(src, rel), "rb").read(), rel
+
+
+def test_checkpoint_loader_roundtrip(tmp_path):
+    """harness.load_checkpoint == the reference's attempt_load steps (models/experimental.py:113-134) on a checkpoint in
+    train.py:882-894's format: the pickled module comes back, fused, in eval mode, and computes the same outputs."""
+    import pytest
+    import torch
+    from mmidet_b200 import harness as H
+    try:
+        ref = H.import_reference()
+    except RuntimeError:
+        pytest.skip("no reference checkout")
+    model = H.build_detector("s", "pytorch", device="cpu").eval()
+    x = torch.rand(1, 3, 64, 64)
+    with torch.no_grad():
+        want = model(x, x)[0][0]
+    path = str(tmp_path / "last.pt")
+    torch.save({"epoch": 3, "model": model, "ema": None, "optimizer": None}, path)
+    got_model = H.load_checkpoint(path, install_path=False)
+    assert not got_model.training
+    assert not any(hasattr(m, "bn") for m in got_model.modules() if type(m) is ref.common.Conv)  # Conv + BN folded
+    with torch.no_grad():
+        got = got_model(x, x)[0][0]
+    assert torch.allclose(got, want, atol=1e-4, rtol=1e-4)
