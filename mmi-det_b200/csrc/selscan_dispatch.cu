@@ -15,7 +15,7 @@ namespace mmi {
 
 bool selscan_use_v2(int B, int L, int ED, int flags) {
     const int cfg = (flags & MMI_FLAG_CFG_MASK) >> MMI_FLAG_CFG_SHIFT;
-    if (cfg == 8) return true;
+    if (cfg == 8 || cfg == 10) return true;
     if (cfg != 0) return false;
     (void)L;
     const int64_t chains = int64_t(B) * ((ED + 31) / 32);
@@ -36,7 +36,7 @@ int selscan_bwd_launch(BwdParams p, int dtype, void *ws, cudaStream_t st) {
 // either way, gains from the second generation (1.224 -> 1.01 ms).
 int selscan_fwd_launch(const FwdParams &p, int dtype, void *ws, cudaStream_t st) {
     const int cfg = (p.flags & MMI_FLAG_CFG_MASK) >> MMI_FLAG_CFG_SHIFT;
-    if (ws && cfg == 8) return selscan_fwd2_launch(p, dtype, ws, st);
+    if (ws && (cfg == 8 || cfg == 10)) return selscan_fwd2_launch(p, dtype, ws, st);
     return selscan_fwd1_launch(p, dtype, ws, st);
 }
 

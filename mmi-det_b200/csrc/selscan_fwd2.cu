@@ -32,8 +32,8 @@ struct Fwd2Maps {
 constexpr int kFB2 = 4;  // steps per exchange block of sweep B
 static_assert(kTC == kChunk, "a chunk starts at a checkpoint");
 
-template <typename T> struct Fwd2Layout {
-    static constexpr int N = kN, STAGES = 3;
+template <typename T, int NW> struct Fwd2Layout {
+    static constexpr int N = kN, STAGES = 3, kNW = NW, kST = NW * kTC;  // (shadow the 8-warp constants of selscan2.cuh)
     static constexpr size_t TILE_BYTES = size_t(kST) * kCH * sizeof(T);
     static constexpr size_t BCT_BYTES = size_t(kST) * N * sizeof(T);
     static constexpr size_t STAGE_BYTES = 3 * TILE_BYTES + 2 * BCT_BYTES;  // x | delta | z (-> out) | B | C
@@ -47,11 +47,12 @@ template <typename T> struct Fwd2Layout {
     static_assert(SMEM <= 232448, "shared memory budget of one CTA per SM");
 };
 
-template <typename T, bool GEOM, bool HAS_Z>
+template <typename T, int NW, bool GEOM, bool HAS_Z>
 __device__ __forceinline__ void fwd2_item(const Fwd2Params &pp, const Fwd2Maps &tm, unsigned char *smem, const float2 (&A2p)[8],
                                           float2 A2b, float2 Dd, int c0, int b, int seg, int chain, int wt, int lane, bool active,
                                           int &g) {
-    using Lay = Fwd2Layout<T>;
+    using Lay = Fwd2Layout<T, NW>;
+    constexpr int kNW = NW, kST = NW * kTC;
     constexpr int N = kN, TC = kTC, ST = kST, CH = kCH;
     const FwdParams &p = pp.f;
     const SegSched &sc = pp.s;
@@ -277,9 +278,9 @@ __device__ __forceinline__ void fwd2_item(const Fwd2Params &pp, const Fwd2Maps &
     }
 }
 
-template <typename T, bool HAS_Z>
-__global__ void __launch_bounds__(kNW * 32, 1) selscan_fwd2_kernel(const Fwd2Params pp, const __grid_constant__ Fwd2Maps tm) {
-    using Lay = Fwd2Layout<T>;
+template <typename T, int NW, bool HAS_Z>
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 1 : 2) selscan_fwd2_kernel(const Fwd2Params pp, const __grid_constant__ Fwd2Maps tm) {
+    using Lay = Fwd2Layout<T, NW>;
     constexpr int N = kN;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + Lay::BAR_OFF);
@@ -319,8 +320,8 @@ __global__ void __launch_bounds__(kNW * 32, 1) selscan_fwd2_kernel(const Fwd2Par
             ok = ok && (fabsf(A2p[k].x - w0) <= 2e-6f * fabsf(w0)) && (fabsf(A2p[k].y - w1) <= 2e-6f * fabsf(w1));
         }
         const bool geom = __syncthreads_and(ok);  // also: everyone has read the ticket before thread 0 takes the next one
-        if (geom) fwd2_item<T, true, HAS_Z>(pp, tm, smem, A2p, A2b, Dd, c0, b, seg, chain, wt, lane, active, g);
-        else fwd2_item<T, false, HAS_Z>(pp, tm, smem, A2p, A2b, Dd, c0, b, seg, chain, wt, lane, active, g);
+        if (geom) fwd2_item<T, NW, true, HAS_Z>(pp, tm, smem, A2p, A2b, Dd, c0, b, seg, chain, wt, lane, active, g);
+        else fwd2_item<T, NW, false, HAS_Z>(pp, tm, smem, A2p, A2b, Dd, c0, b, seg, chain, wt, lane, active, g);
     }
     if (tid == 0) bulk_wait_read<0>();  // shared memory must outlive the last tile store's reads
 }
@@ -334,10 +335,11 @@ int64_t selscan_fwd2_ws_bytes(int B, int L, int ED) {
     return int64_t(al256f(16 + size_t(nch) * 4)) + nch * 8 * 32 * 8;
 }
 
-template <typename T, bool HAS_Z> static int launch_fwd2_t(Fwd2Params pp, int dtype, void *ws, cudaStream_t st) {
-    using Lay = Fwd2Layout<T>;
+template <typename T, int NW, bool HAS_Z> static int launch_fwd2_t(Fwd2Params pp, int dtype, void *ws, cudaStream_t st) {
+    using Lay = Fwd2Layout<T, NW>;
+    constexpr int kNW = NW, kST = NW * kTC;
     FwdParams &p = pp.f;
-    auto kern = selscan_fwd2_kernel<T, HAS_Z>;
+    auto kern = selscan_fwd2_kernel<T, NW, HAS_Z>;
     static thread_local int attr_dev = -1;  // the opt-in is per device and sticky: set it once, not on every launch
     int dev = 0;
     cudaGetDevice(&dev);
@@ -353,6 +355,14 @@ template <typename T, bool HAS_Z> static int launch_fwd2_t(Fwd2Params pp, int dt
     }
     if (int e = seg_sched_plan(p.B, p.L, p.ED, p.flags, &pp.s)) return e;
     SegSched &sc = pp.s;
+    if (NW != 8) {  // two CTAs per SM: more resident CTAs than chains, so chaining segments cannot add parallelism; re-plan
+        const int ntiles = (p.L + kST - 1) / kST;  // on this variant's super-tile with the forced segment count only
+        int nseg = (p.flags & MMI_FLAG_NSEG_MASK) >> MMI_FLAG_NSEG_SHIFT;
+        nseg = std::max(1, std::min({nseg ? nseg : 1, 16, ntiles}));
+        sc.seg_tiles = (ntiles + nseg - 1) / nseg;
+        sc.nseg = (ntiles + sc.seg_tiles - 1) / sc.seg_tiles;
+        sc.nitems = sc.nchains * sc.nseg;
+    }
     sc.ticket = static_cast<unsigned *>(ws);
     sc.done = sc.ticket + 4;
     const size_t hdr = al256f(16 + size_t(sc.nchains) * 4);
@@ -368,7 +378,7 @@ template <typename T, bool HAS_Z> static int launch_fwd2_t(Fwd2Params pp, int dt
     if (int e = make_tmap_3d(&tm.C, p.Cm, dtype, nb, L, kN, kN * sizeof(T), kST, kN)) return e;
     if (int e = make_tmap_3d(&tm.o, p.out, dtype, nb, L, p.ED, p.o_ld * sizeof(T), kST, kCH)) return e;
     if (int e = check_cuda(cudaMemsetAsync(ws, 0, hdr, st), "selscan_fwd2 ticket memset")) return e;
-    const int grid = std::min(sc.nitems, sm_count());
+    const int grid = std::min(sc.nitems, sm_count() * (NW == 8 ? 1 : 2));
     kern<<<grid, kNW * 32, Lay::SMEM, st>>>(pp, tm);
     return check_cuda(cudaGetLastError(), "selscan_fwd2 launch");
 }
@@ -378,12 +388,16 @@ int selscan_fwd2_launch(const FwdParams &p, int dtype, void *ws, cudaStream_t st
     memset(&pp, 0, sizeof(pp));
     pp.f = p;
     const bool z = p.z != nullptr;
+    const bool four = ((p.flags & MMI_FLAG_CFG_MASK) >> MMI_FLAG_CFG_SHIFT) == 10;  // 4 chunk-warps, two CTAs per SM
+#define MMI_FWD2(T)                                                                                           \
+    return four ? (z ? launch_fwd2_t<T, 4, true>(pp, dtype, ws, st) : launch_fwd2_t<T, 4, false>(pp, dtype, ws, st)) \
+                : (z ? launch_fwd2_t<T, 8, true>(pp, dtype, ws, st) : launch_fwd2_t<T, 8, false>(pp, dtype, ws, st))
     switch (dtype) {
-        case MMI_F32: return z ? launch_fwd2_t<float, true>(pp, dtype, ws, st) : launch_fwd2_t<float, false>(pp, dtype, ws, st);
-        case MMI_BF16:
-            return z ? launch_fwd2_t<__nv_bfloat16, true>(pp, dtype, ws, st) : launch_fwd2_t<__nv_bfloat16, false>(pp, dtype, ws, st);
-        case MMI_F16: return z ? launch_fwd2_t<__half, true>(pp, dtype, ws, st) : launch_fwd2_t<__half, false>(pp, dtype, ws, st);
+        case MMI_F32: MMI_FWD2(float);
+        case MMI_BF16: MMI_FWD2(__nv_bfloat16);
+        case MMI_F16: MMI_FWD2(__half);
     }
+#undef MMI_FWD2
     set_error("selscan_fwd2: unknown dtype %d", dtype);
     return MMI_ERR_ARG;
 }

@@ -175,9 +175,10 @@ def test_v2_kernels_stay_inside_their_outputs(shape, dtype):
         assert bool(torch.isfinite(t.float()).all())
 
 
+@pytest.mark.parametrize("variant", [8, 10])  # 8 chunk-warps / one CTA per SM; 4 chunk-warps / two CTAs per SM
 @pytest.mark.parametrize("nseg", [0, 1, 3])
 @pytest.mark.parametrize("random_A", [False, True])
-def test_v2_forward_matches_first_generation(nseg, random_A):
+def test_v2_forward_matches_first_generation(nseg, random_A, variant):
     """outputs, final state hT and checkpoints of the second-generation forward == the first generation's, with a non-zero
     h0, a ragged tail and chained segments; and h0 -> hT chaining over a cut equals one call."""
     from mmidet_b200 import ops
@@ -188,7 +189,8 @@ def test_v2_forward_matches_first_generation(nseg, random_A):
     run = lambda fl, **kw: ops.selscan_fwd_raw(a["x"], a["delta"], a["A"], a["Bm"], a["Cm"], a["D"], z=a["z"], want_state=True,
                                                want_chk=True, flags=fl, **kw)
     o1, hT1, chk1, _ = run(9 << 4, h0=h0)
-    o2, hT2, chk2, _ = run(V2 | (nseg << 8), h0=h0)
+    V2v = variant << 4
+    o2, hT2, chk2, _ = run(V2v | (nseg << 8), h0=h0)
     for u, v in ((o1, o2), (hT1, hT2), (chk1, chk2)):
         assert relerr(v.cpu().numpy(), u.cpu().numpy()) <= 2e-5
     ref_out, ref_h = O.selective_scan_fwd(inp["x"], inp["delta"], inp["A"], inp["Bm"], inp["Cm"], inp["D"], z=inp["z"],
@@ -197,10 +199,10 @@ def test_v2_forward_matches_first_generation(nseg, random_A):
     cut = 517
     sl = lambda t, s: t[:, s].contiguous()
     first = ops.selscan_fwd_raw(sl(a["x"], slice(0, cut)), sl(a["delta"], slice(0, cut)), a["A"], sl(a["Bm"], slice(0, cut)),
-                                sl(a["Cm"], slice(0, cut)), a["D"], z=sl(a["z"], slice(0, cut)), h0=h0, want_state=True, flags=V2)
+                                sl(a["Cm"], slice(0, cut)), a["D"], z=sl(a["z"], slice(0, cut)), h0=h0, want_state=True, flags=V2v)
     second = ops.selscan_fwd_raw(sl(a["x"], slice(cut, L)), sl(a["delta"], slice(cut, L)), a["A"], sl(a["Bm"], slice(cut, L)),
                                  sl(a["Cm"], slice(cut, L)), a["D"], z=sl(a["z"], slice(cut, L)), h0=first[1], want_state=True,
-                                 flags=V2)
+                                 flags=V2v)
     assert relerr(torch.cat([first[0], second[0]], 1).cpu().numpy(), o2.cpu().numpy()) <= 1e-5
     assert relerr(second[1].cpu().numpy(), hT2.cpu().numpy()) <= 1e-5
 
