@@ -111,3 +111,28 @@ def test_checkpoint_loader_roundtrip(tmp_path):
     with torch.no_grad():
         got = got_model(x, x)[0][0]
     assert torch.allclose(got, want, atol=1e-4, rtol=1e-4)
+
+
+def test_harness_optimizer_groups_follow_the_reference_quirk():
+    """train.py:572-579 groups parameters by MODULE attribute: bare nn.Parameters (MambaBlock.A_log / D) land in no group
+    and are never updated -- the harness keeps that, which is why A stays on the geometric fast path."""
+    import pytest
+    import torch
+    from mmidet_b200 import harness as H
+    try:
+        H.import_reference()
+    except RuntimeError:
+        pytest.skip("no reference checkout")
+    model = H.build_detector("s", "pytorch", device="cpu")
+    hyp = H.scale_hyp(model, 6, 640)
+    opt = H.make_optimizer(model, hyp, 16)
+    in_groups = {id(p) for g in opt.param_groups for p in g["params"]}
+    names = dict(model.named_parameters())
+    bare = [n for n in names if n.endswith("A_log") or n.endswith(".D")]
+    assert len(bare) == 8  # four fusion sites x (A_log, D)
+    assert all(id(names[n]) not in in_groups for n in bare)
+    assert all(id(p) in in_groups for n, p in names.items() if n.endswith("in_proj.weight") or n.endswith("conv1d.bias"))
+    assert len(opt.param_groups) == 3 and opt.param_groups[1]["weight_decay"] > 0 and opt.param_groups[0]["nesterov"]
+    imgs, targets = H.synthetic_batch(3, 64, device="cpu", seed=1)
+    assert imgs.dtype == torch.uint8 and tuple(imgs.shape) == (3, 6, 64, 64)
+    assert targets.shape[1] == 6 and float(targets[:, 0].max()) == 2.0 and float(targets[:, 2:].max()) <= 1.0

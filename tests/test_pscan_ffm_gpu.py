@@ -75,6 +75,27 @@ def test_pscan_fp64_multi_segment():
     assert relerr(gA.cpu().numpy(), gA64) <= 1e-12 and relerr(gX.cpu().numpy(), gX64) <= 1e-12
 
 
+def test_pscan_config0_shape():
+    """BASELINE configs[0] as the materialised parity API: (B, L, D, N) = (2, 6400, 256, 16), 210 MB per tensor, ~70 segments per
+    sequence (forward and reverse); values against the sequential fp64 oracle."""
+    from mmidet_b200.pscan import pscan
+    rng = np.random.default_rng(9)
+    shape = (2, 6400, 256, 16)
+    A = (rng.random(shape, dtype=np.float32) * 0.3 + 0.7)
+    X = rng.standard_normal(shape, dtype=np.float32)
+    gH = rng.standard_normal(shape, dtype=np.float32)
+    At, Xt = _t(A).requires_grad_(True), _t(X).requires_grad_(True)
+    H = pscan(At, Xt)
+    gA, gX = torch.autograd.grad(H, (At, Xt), _t(gH))
+    for b in range(2):  # one batch entry at a time keeps the fp64 oracle's footprint small
+        A64, X64, g64 = A[b:b + 1].astype(np.float64), X[b:b + 1].astype(np.float64), gH[b:b + 1].astype(np.float64)
+        H64 = O.pscan_seq_fwd(A64, X64)
+        gA64, gX64 = O.pscan_seq_bwd(A64, H64, g64)
+        assert relerr(H[b:b + 1].detach().cpu().numpy(), H64) <= 1e-4
+        assert relerr(gA[b:b + 1].cpu().numpy(), gA64) <= 1e-4
+        assert relerr(gX[b:b + 1].cpu().numpy(), gX64) <= 1e-4
+
+
 @pytest.mark.parametrize("tag", ["80x80", "160x160", "96x72"])
 def test_ffm_large_maps_vs_reference_golden(golden, tag):
     """extract_frequency2 above 64 x 64 (H in {8, 16, 20, 80, 160}): the kept-bin projection kernel
