@@ -35,10 +35,12 @@ enum {
     MMI_FLAG_NO_GEOM = 1,      /* disable the geometric-A fast path (A[d,n] == (n+1)*A[d,0], the S4D-real init) */
     MMI_FLAG_DELTA_SOFTPLUS = 2, /* `delta` holds the pre-activation dt_proj(.) (models/mamba.py:203): the kernels apply softplus
                                   on load and the backward returns the gradient w.r.t. the pre-activation */
-    MMI_FLAG_CFG_SHIFT = 4,    /* bits 4..7: pick a CTA shape (channel warps x time warps x stages) for tuning runs; */
-    MMI_FLAG_CFG_MASK = 0xF0,  /*            0 = default.  Results do not depend on it.                                */
-    MMI_FLAG_NSEG_SHIFT = 8,   /* bits 8..15: force the number of L segments of the forward (1..32); 0 = heuristic */
-    MMI_FLAG_NSEG_MASK = 0xFF00
+    MMI_FLAG_CFG_SHIFT = 4,    /* bits 4..7: kernel selection for tuning runs and tests; 0 = default dispatch (results do not   */
+    MMI_FLAG_CFG_MASK = 0xF0,  /*            depend on it).  1..6: first-generation forward CTA shapes; 8: second-generation      */
+                               /*            kernels (persistent grid over chained L segments) for forward and backward; 9: first  */
+                               /*            generation for both; 10: as 8 with the 4-warp / two-CTA forward.                      */
+    MMI_FLAG_NSEG_SHIFT = 8,   /* bits 8..15: force the number of L segments per sequence (first generation: published summaries, */
+    MMI_FLAG_NSEG_MASK = 0xFF00 /*           1..32; second generation: chained hand-off, 1..16); 0 = heuristic                     */
 };
 
 const char *mmi_last_error(void);

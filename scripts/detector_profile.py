@@ -16,10 +16,12 @@ ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--imgsz", type=int, default=640)
 ap.add_argument("--arm", default="ours")
 ap.add_argument("--mode", default="train")
+ap.add_argument("--channels-last", dest="cl", action="store_true")
+ap.add_argument("--rows", type=int, default=45)
 a = ap.parse_args()
 from mmidet_b200 import harness as H  # noqa: E402
 
-model = H.build_detector(a.size, a.arm, seed=0)
+model = H.build_detector(a.size, a.arm, seed=0, channels_last=a.cl and a.mode == "train")
 ref = H.import_reference()
 imgs, targets = H.synthetic_batch(a.batch, a.imgsz, seed=1)
 if a.mode == "train":
@@ -29,7 +31,7 @@ if a.mode == "train":
     opt = H.make_optimizer(model, hyp, a.batch)
     step = lambda: H.train_step(model, cl, opt, imgs, targets, autocast_dtype=torch.bfloat16, fused_prep=a.arm == "ours")
 else:
-    model.eval().half()
+    model = H.prepare_inference(model, torch.float16, channels_last=a.cl)
     from mmidet_b200 import postprocess
     postprocess.install_detect(ref.yolo_test)
 
@@ -49,4 +51,4 @@ print(f"wall per step: {(time.perf_counter() - t0) / 3 * 1e3:.1f} ms")
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     step()
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=a.rows, max_name_column_width=70))
