@@ -92,6 +92,19 @@ class MambaBlock(nn.Module):
         self.D = nn.Parameter(torch.ones(c.d_inner))
         self.out_proj = nn.Linear(c.d_inner, c.d_model, bias=c.bias)
 
+    def _apply(self, fn, recurse=True):
+        """`.half()` / `.bfloat16()` (detect_twostream.py:45, test.py:68) keep A_log and D in fp32: both are only ever used
+        up-cast (`A_log.float()`, `D.float()`, models/mamba.py:196-197), and rounding log(1..N) to 16 bits would move every row
+        of A off the S4D-real geometric form -- the model would drift from its fp32 self and the scan would need N exponentials
+        per step instead of one.  Device moves and fp32 / fp64 casts apply to them as to any parameter."""
+        keep = {n: getattr(self, n).data for n in ("A_log", "D") if getattr(self, n, None) is not None}
+        out = super()._apply(fn, recurse)
+        for n, v in keep.items():
+            p = getattr(self, n)
+            if p.dtype in (torch.float16, torch.bfloat16) and v.dtype == torch.float32:
+                p.data = v.to(p.device)
+        return out
+
     # -- the hot path -----------------------------------------------------------------------------------------
     def selective_scan(self, x, delta, A, B, C, D, z=None, delta_softplus=False):
         """models/mamba.py:212-233 (and :235-265, same maths) on the fused kernel; `z` additionally fuses the gate,

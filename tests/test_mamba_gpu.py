@@ -84,6 +84,8 @@ def test_block_is_half_clean(dtype):
     x = torch.randn(2, 100, 32, device="cuda")
     ref = blk(x).detach()
     low = blk.to(dtype)
+    assert low.A_log.dtype == torch.float32 and low.D.dtype == torch.float32  # fp32 masters survive .half() / .bfloat16()
+    assert low.in_proj.weight.dtype == dtype
     out = low(x.to(dtype))
     assert out.dtype == dtype
     assert relerr(out.detach().float().cpu().numpy(), ref.cpu().numpy()) <= 3e-2
