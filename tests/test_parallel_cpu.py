@@ -65,3 +65,54 @@ def test_shard_partitions_exactly(n, world):
     assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
     sizes = [b - a for a, b in spans]
     assert max(sizes) - min(sizes) <= 1
+
+
+def _detector_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.set_num_threads(2)
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from mmidet_b200 import harness as H
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ref = H.import_reference()
+        model = H.build_detector("s", "pytorch", seed=0, device="cpu").train()  # the reference's own blocks: runs on CPU
+        hyp = H.scale_hyp(model, 6, 64)
+        loss_fn = ref.loss.ComputeLoss(model)
+        opt = H.make_optimizer(model, hyp, 2 * world)
+        net = DDP(model, bucket_cap_mb=8, gradient_as_bucket_view=True, broadcast_buffers=False)
+        imgs, targets = H.synthetic_batch(2, 64, seed=100 + rank, device="cpu")
+        w0 = model.model[0].conv.conv.weight.detach().clone()
+        f = imgs.float() / 255.0
+        pred, comb = net(f[:, :3], f[:, 3:])
+        loss, _ = loss_fn(pred, targets, comb.reshape(-1))
+        (loss * world).backward()  # train.py:790-791
+        g = model.model[0].conv.conv.weight.grad.detach().clone()
+        opt.step()
+        q.put((rank, float(loss), g.double().sum().item(), g.double().abs().sum().item(),
+               float((model.model[0].conv.conv.weight.detach() - w0).abs().max())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_detector_ddp_step_two_rank_gloo():
+    """BASELINE configs[3] in miniature on CPU: the harness's DDP training step (unmodified reference Model / ComputeLoss,
+    different synthetic batches per rank, loss * world_size, 8 MB buckets) on two gloo ranks: both ranks end up with the
+    same all-reduced gradient and the optimizer moves the weights."""
+    from mmidet_b200 import harness as H
+    try:
+        H.locate_reference()
+    except RuntimeError:
+        pytest.skip("no reference checkout")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_detector_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+        assert p.exitcode == 0
+    got = sorted(q.get(timeout=5) for _ in range(2))
+    assert got[0][1] != got[1][1]  # different batches, different local losses
+    assert abs(got[0][2] - got[1][2]) <= 1e-9 * max(1.0, abs(got[0][2])) and abs(got[0][3] - got[1][3]) <= 1e-9 * got[0][3]
+    assert got[0][4] > 0 and got[1][4] > 0
