@@ -18,7 +18,7 @@ need the reference detector, which does not travel to the GPU box; they are pari
   cpu_baseline / --impl reference: the UNMODIFIED reference's own CPU path (MambaBlock.selective_scan + gate + autograd,
             imported from the staged checkout baseline/_ref) on a bounded sample of the same workload, all host cores
             (kind "reference"); where the checkout is not staged, the C + OpenMP oracle port (kind "port"), which is also
-            reported as `cpu_port` for context (it is ~15x faster than the reference's PyTorch path).
+            reported as `cpu_port` for context (it is ~5x faster than the reference's PyTorch path on 16 cores).
   parity_relerr   batch entry 0 of the timed step's outputs against the fp64 oracle (the checker, after the timed region).
   general_A / bf16   the same step with a trained (non-geometric) A, and with bf16 I/O: what a training run sees after the
             first optimizer step / under autocast (secondary legs, a few steps each).
