@@ -18,8 +18,10 @@ bool selscan_use_v2(int B, int L, int ED, int flags) {
     if (cfg == 8 || cfg == 10) return true;
     if (cfg != 0) return false;
     (void)L;
+    // measured crossover (profiles/r02_scan_generations.txt): a second-generation CTA takes the same time per chain however
+    // few chains there are, the first generation splits L to fill the GPU -- 64 chains: 0.405 vs 0.543 ms, 128: 0.771 vs 0.557 ms
     const int64_t chains = int64_t(B) * ((ED + 31) / 32);
-    return chains * 2 >= sm_count();
+    return chains * 3 >= 2 * int64_t(sm_count());
 }
 
 int64_t selscan_bwd_ws_bytes(int B, int L, int ED) { return std::max(selscan_bwd1_ws_bytes(B, L, ED), selscan_bwd2_ws_bytes(B, L, ED)); }
