@@ -1,7 +1,7 @@
 // selscan_dispatch.cu -- which generation of the scan kernels a call takes.
 //
 //   second generation (selscan_fwd2.cu / selscan_bwd2.cu): persistent grid over (32-channel chain, L segment) items; needs
-//       enough independent chains to occupy the GPU -- the training shapes (B * ceil(ED / 32) >= half the SMs)
+//       enough independent chains to occupy the GPU -- the training shapes (B * ceil(ED / 32) >= two thirds of the SMs)
 //   first generation (selscan_fwd.cu / selscan_bwd.cu): one CTA per 32 / 64-channel tile, L split across CTAs with published
 //       segment summaries (decoupled look-back) -- small batches and inference, where only splitting L can fill the GPU
 // MMI_FLAG_CFG bits: 8 forces the second generation, 9 the first, 1..6 are first-generation CTA shapes (tuning / tests).
