@@ -166,6 +166,17 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    # MMIDET_SO=<path>: load exactly this build of the library (kernel tuning / ablation builds, profiles/r02_scan_generations.txt).
+    # A missing or incomplete file raises -- there is no fallback behind it either.
+    override = os.environ.get("MMIDET_SO")
+    if override:
+        lib = ctypes.CDLL(override)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
     if needs_build():
         # a source newer than the library must compile: never run yesterday's binary against today's sources.  The one
         # exception is a box without nvcc (the library was built elsewhere and shipped): then the shipped file is loaded.
