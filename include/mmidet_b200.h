@@ -38,7 +38,8 @@ enum {
     MMI_FLAG_CFG_SHIFT = 4,    /* bits 4..7: kernel selection for tuning runs and tests; 0 = default dispatch (results do not   */
     MMI_FLAG_CFG_MASK = 0xF0,  /*            depend on it).  1..6: first-generation forward CTA shapes; 8: second-generation      */
                                /*            kernels (persistent grid over chained L segments) for forward and backward; 9: first  */
-                               /*            generation for both; 10: as 8 with the 4-warp / two-CTA forward.                      */
+                               /*            generation for both; 10: as 8 with the 4-warp / two-CTA forward; 11: default forward, */
+                               /*            16-warp second-generation backward (selscan_bwd3.cu).                                 */
     MMI_FLAG_NSEG_SHIFT = 8,   /* bits 8..15: force the number of L segments per sequence (first generation: published summaries, */
     MMI_FLAG_NSEG_MASK = 0xFF00 /*           1..32; second generation: chained hand-off, 1..16); 0 = heuristic                     */
 };

@@ -67,6 +67,7 @@ int selscan_fwd2_launch(const FwdParams &p, int dtype, void *ws, cudaStream_t st
 int64_t selscan_fwd2_ws_bytes(int B, int L, int ED);
 int selscan_bwd2_launch(const BwdParams &p, int dtype, void *ws, cudaStream_t st);
 int64_t selscan_bwd2_ws_bytes(int B, int L, int ED);
+int selscan_bwd3_launch(const BwdParams &p, int dtype, void *ws, cudaStream_t st);  // 16-warp form, same workspace as bwd2
 bool selscan_use_v2(int B, int L, int ED, int flags);  // which generation a call takes (shape heuristic, MMI_FLAG_CFG override)
 int seg_sched_plan(int B, int L, int ED, int flags, SegSched *s);  // fills nseg / seg_tiles / ntile_c / nchains / nitems
 

@@ -17,7 +17,17 @@
 #pragma once
 #include "common.cuh"
 
+#include "selscan.h"
+
 namespace mmi {
+
+// host side shared by selscan_bwd2.cu and selscan_bwd3.cu (defined in selscan_bwd2.cu)
+struct Bwd2Maps {
+    CUtensorMap x, d, z, g, B, C, odx, odd, odz;
+};
+int bwd2_prepare(Bwd2Params &pp, Bwd2Maps &tm, int dtype, void *ws, cudaStream_t st);  // plan, workspace, tensor maps, ticket reset
+int bwd2_finish(const Bwd2Params &pp, int dtype, cudaStream_t st);                     // deterministic reduction of the partials
+
 namespace v2 {
 
 constexpr int kCH = 32;    // channels per chain
@@ -41,6 +51,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float2 (&v)[8]) {
           "=f"(v[4].x), "=f"(v[4].y), "=f"(v[5].x), "=f"(v[5].y), "=f"(v[6].x), "=f"(v[6].y), "=f"(v[7].x), "=f"(v[7].y)
         : "r"(taddr)
         : "memory");
+}
+// 8 fp32 per thread per op (the 16-warp backward: 4 states x 2 channels per lane)
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float2 (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "f"(v[0].x), "f"(v[0].y),
+                 "f"(v[1].x), "f"(v[1].y), "f"(v[2].x), "f"(v[2].y), "f"(v[3].x), "f"(v[3].y)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float2 (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x), "=f"(v[3].y)
+                 : "r"(taddr)
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -112,6 +134,27 @@ __device__ __forceinline__ void decay8f(float2 dv, float2 A2b, const float2 (&A2
         for (int k = 0; k < 8; ++k) {
             const float2 e = mul2(dv, A2p[k]);
             a[k] = mul2(make_float2(ex2(e.x), ex2(e.y)), fac);
+        }
+    }
+}
+
+// 4 states per lane (state quarter q): a[k] = exp(dv * A[., 4 q + k]).  GEOM: a[0] = exp2(dv * A2q) with A2q = (4 q + 1) A2b
+// evaluated directly, the other three by powers of R = exp2(dv * A2b) -- 4 exponentials + 5 packed multiplies per step.
+template <bool GEOM>
+__device__ __forceinline__ void decay4(float2 dv, float2 A2b, float2 A2q, const float2 (&A2p)[4], float2 (&a)[4]) {
+    if constexpr (GEOM) {
+        const float2 e = mul2(dv, A2b), e1 = mul2(dv, A2q);
+        const float2 R = make_float2(ex2(e.x), ex2(e.y));
+        a[0] = make_float2(ex2(e1.x), ex2(e1.y));
+        const float2 R2 = mul2(R, R);
+        a[1] = mul2(a[0], R);
+        a[2] = mul2(a[0], R2);
+        a[3] = mul2(a[1], R2);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 e = mul2(dv, A2p[k]);
+            a[k] = make_float2(ex2(e.x), ex2(e.y));
         }
     }
 }

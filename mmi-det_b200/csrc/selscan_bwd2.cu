@@ -30,10 +30,6 @@ namespace mmi {
 
 using namespace v2;
 
-struct Bwd2Maps {
-    CUtensorMap x, d, z, g, B, C, odx, odd, odz;
-};
-
 constexpr int kRB2 = 4;  // steps per cross-channel reduction block
 
 template <typename T> struct Bwd2Layout {
@@ -560,19 +556,12 @@ int64_t selscan_bwd2_ws_bytes(int B, int L, int ED) {
            int64_t(al256(16 + size_t(nch) * 4)) + nch * 8 * 32 * 8;
 }
 
-template <typename T, bool HAS_Z> static int launch_bwd2_t(Bwd2Params pp, int dtype, void *ws, cudaStream_t st) {
-    using Lay = Bwd2Layout<T>;
+// Host side shared by the 8-warp and the 16-warp kernel (selscan_bwd3.cu): plan the segments, carve the workspace, encode
+// the tensor maps, clear the ticket / flags.
+int bwd2_prepare(Bwd2Params &pp, Bwd2Maps &tm, int dtype, void *ws, cudaStream_t st) {
     BwdParams &p = pp.b;
-    auto kern = selscan_bwd2_kernel<T, HAS_Z>;
-    static thread_local int attr_dev = -1;  // the opt-in is per device and sticky: set it once, not on every launch
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (attr_dev != dev) {
-        if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Lay::SMEM)),
-                               "selscan_bwd2 smem attribute"))
-            return e;
-        attr_dev = dev;
-    }
+    const size_t es = dtype == MMI_F32 ? 4 : 2;
+    const bool has_z = p.z != nullptr;
     const uint64_t rows = uint64_t(p.B) * p.L, nb = p.B, L = p.L;
     if (int e = seg_sched_plan(p.B, p.L, p.ED, p.flags, &pp.s)) return e;
     SegSched &sc = pp.s;
@@ -586,28 +575,56 @@ template <typename T, bool HAS_Z> static int launch_bwd2_t(Bwd2Params pp, int dt
     sc.done = sc.ticket + 4;
     const size_t hdr = al256(16 + size_t(sc.nchains) * 4);
     sc.carry = reinterpret_cast<float *>(w + hdr);
-    Bwd2Maps tm;
     memset(&tm, 0, sizeof(tm));
-    if (int e = make_tmap_3d(&tm.x, p.x, dtype, nb, L, p.ED, p.x_ld * sizeof(T), kST, kCH)) return e;
-    if (int e = make_tmap_3d(&tm.d, p.delta, dtype, nb, L, p.ED, p.d_ld * sizeof(T), kST, kCH)) return e;
-    if (int e = make_tmap_3d(&tm.g, p.dout, dtype, nb, L, p.ED, p.g_ld * sizeof(T), kST, kCH)) return e;
-    if (HAS_Z)
-        if (int e = make_tmap_3d(&tm.z, p.z, dtype, nb, L, p.ED, p.z_ld * sizeof(T), kST, kCH)) return e;
-    if (int e = make_tmap_3d(&tm.B, p.Bm, dtype, nb, L, kN, kN * sizeof(T), kST, kN)) return e;
-    if (int e = make_tmap_3d(&tm.C, p.Cm, dtype, nb, L, kN, kN * sizeof(T), kST, kN)) return e;
-    if (int e = make_tmap_3d(&tm.odx, p.dx, dtype, nb, L, p.ED, p.ED * sizeof(T), kST, kCH)) return e;
-    if (int e = make_tmap_3d(&tm.odd, p.ddelta, dtype, nb, L, p.ED, p.ED * sizeof(T), kST, kCH)) return e;
-    if (HAS_Z)
-        if (int e = make_tmap_3d(&tm.odz, p.dz, dtype, nb, L, p.ED, p.ED * sizeof(T), kST, kCH)) return e;
-    if (int e = check_cuda(cudaMemsetAsync(sc.ticket, 0, hdr, st), "selscan_bwd2 ticket memset")) return e;
-    const int grid = std::min(sc.nitems, sm_count());
+    if (int e = make_tmap_3d(&tm.x, p.x, dtype, nb, L, p.ED, p.x_ld * es, kST, kCH)) return e;
+    if (int e = make_tmap_3d(&tm.d, p.delta, dtype, nb, L, p.ED, p.d_ld * es, kST, kCH)) return e;
+    if (int e = make_tmap_3d(&tm.g, p.dout, dtype, nb, L, p.ED, p.g_ld * es, kST, kCH)) return e;
+    if (has_z)
+        if (int e = make_tmap_3d(&tm.z, p.z, dtype, nb, L, p.ED, p.z_ld * es, kST, kCH)) return e;
+    if (int e = make_tmap_3d(&tm.B, p.Bm, dtype, nb, L, kN, kN * es, kST, kN)) return e;
+    if (int e = make_tmap_3d(&tm.C, p.Cm, dtype, nb, L, kN, kN * es, kST, kN)) return e;
+    if (int e = make_tmap_3d(&tm.odx, p.dx, dtype, nb, L, p.ED, p.ED * es, kST, kCH)) return e;
+    if (int e = make_tmap_3d(&tm.odd, p.ddelta, dtype, nb, L, p.ED, p.ED * es, kST, kCH)) return e;
+    if (has_z)
+        if (int e = make_tmap_3d(&tm.odz, p.dz, dtype, nb, L, p.ED, p.ED * es, kST, kCH)) return e;
+    return check_cuda(cudaMemsetAsync(sc.ticket, 0, hdr, st), "selscan_bwd2 ticket memset");
+}
+
+template <typename T> static int finish_t(const Bwd2Params &pp, cudaStream_t st) {
+    const BwdParams &p = pp.b;
+    const int64_t rows = int64_t(p.B) * p.L, work = rows * 8 + int64_t(p.ED) * (kN + 1);
+    selscan_bwd2_finish_kernel<T><<<unsigned((work + 255) / 256), 256, 0, st>>>(
+        p.ws_bc, p.ws_ad, static_cast<T *>(p.dBm), static_cast<T *>(p.dCm), p.dA, p.dD, rows, pp.s.ntile_c, p.B * pp.s.nseg, p.ED);
+    return check_cuda(cudaGetLastError(), "selscan_bwd2 finish launch");
+}
+int bwd2_finish(const Bwd2Params &pp, int dtype, cudaStream_t st) {
+    switch (dtype) {
+        case MMI_F32: return finish_t<float>(pp, st);
+        case MMI_BF16: return finish_t<__nv_bfloat16>(pp, st);
+        case MMI_F16: return finish_t<__half>(pp, st);
+    }
+    set_error("selscan_bwd2: unknown dtype %d", dtype);
+    return MMI_ERR_ARG;
+}
+
+template <typename T, bool HAS_Z> static int launch_bwd2_t(Bwd2Params pp, int dtype, void *ws, cudaStream_t st) {
+    using Lay = Bwd2Layout<T>;
+    auto kern = selscan_bwd2_kernel<T, HAS_Z>;
+    static thread_local int attr_dev = -1;  // the opt-in is per device and sticky: set it once, not on every launch
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (attr_dev != dev) {
+        if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Lay::SMEM)),
+                               "selscan_bwd2 smem attribute"))
+            return e;
+        attr_dev = dev;
+    }
+    Bwd2Maps tm;
+    if (int e = bwd2_prepare(pp, tm, dtype, ws, st)) return e;
+    const int grid = std::min(pp.s.nitems, sm_count());
     kern<<<grid, kNW * 32, Lay::SMEM, st>>>(pp, tm);
     if (int e = check_cuda(cudaGetLastError(), "selscan_bwd2 launch")) return e;
-    const int64_t work = int64_t(rows) * 8 + int64_t(p.ED) * (kN + 1);
-    selscan_bwd2_finish_kernel<T><<<unsigned((work + 255) / 256), 256, 0, st>>>(
-        p.ws_bc, p.ws_ad, static_cast<T *>(p.dBm), static_cast<T *>(p.dCm), p.dA, p.dD, int64_t(rows), sc.ntile_c,
-        p.B * sc.nseg, p.ED);
-    return check_cuda(cudaGetLastError(), "selscan_bwd2 finish launch");
+    return bwd2_finish(pp, dtype, st);
 }
 
 int selscan_bwd2_launch(const BwdParams &p, int dtype, void *ws, cudaStream_t st) {

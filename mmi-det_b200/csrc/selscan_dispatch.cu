@@ -4,7 +4,8 @@
 //       enough independent chains to occupy the GPU -- the training shapes (B * ceil(ED / 32) >= two thirds of the SMs)
 //   first generation (selscan_fwd.cu / selscan_bwd.cu): one CTA per 32 / 64-channel tile, L split across CTAs with published
 //       segment summaries (decoupled look-back) -- small batches and inference, where only splitting L can fill the GPU
-// MMI_FLAG_CFG bits: 8 forces the second generation, 9 the first, 1..6 are first-generation CTA shapes (tuning / tests).
+// MMI_FLAG_CFG bits: 8 forces the second generation, 9 the first, 1..6 are first-generation CTA shapes, 10 the 4-warp second-
+// generation forward, 11 the 16-warp backward (selscan_bwd3.cu: measured slower, kept as the tested counter-example) -- tuning / tests.
 #include <algorithm>
 
 #include "../../include/mmidet_b200.h"
@@ -15,7 +16,7 @@ namespace mmi {
 
 bool selscan_use_v2(int B, int L, int ED, int flags) {
     const int cfg = (flags & MMI_FLAG_CFG_MASK) >> MMI_FLAG_CFG_SHIFT;
-    if (cfg == 8 || cfg == 10) return true;
+    if (cfg == 8 || cfg == 10 || cfg == 11) return true;
     if (cfg != 0) return false;
     (void)L;
     // measured crossover (profiles/r02_scan_generations.txt): a second-generation CTA takes the same time per chain however
@@ -28,6 +29,8 @@ int64_t selscan_bwd_ws_bytes(int B, int L, int ED) { return std::max(selscan_bwd
 int64_t selscan_fwd_ws_bytes(int B, int ED) { return std::max(selscan_fwd1_ws_bytes(B, ED), selscan_fwd2_ws_bytes(B, 0, ED)); }
 
 int selscan_bwd_launch(BwdParams p, int dtype, void *ws, cudaStream_t st) {
+    const int cfg = (p.flags & MMI_FLAG_CFG_MASK) >> MMI_FLAG_CFG_SHIFT;
+    if (cfg == 11) return selscan_bwd3_launch(p, dtype, ws, st);
     if (selscan_use_v2(p.B, p.L, p.ED, p.flags)) return selscan_bwd2_launch(p, dtype, ws, st);
     return selscan_bwd1_launch(p, dtype, ws, st);
 }

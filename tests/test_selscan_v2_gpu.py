@@ -1,6 +1,7 @@
-"""GPU parity of the second-generation scan kernels (selscan_fwd2.cu / selscan_bwd2.cu: persistent grid over
-(32-channel chain, L segment) items, lanes split the states in halves, chained segments) forced with MMI_FLAG_CFG = 8 on
-shapes that would otherwise take the first generation: values against the fp64 C oracle.
+"""GPU parity of the second-generation scan kernels (selscan_fwd2.cu / selscan_bwd2.cu / selscan_bwd3.cu: persistent grid
+over (32-channel chain, L segment) items, lanes split the states in halves or quarters, chained segments) forced with
+MMI_FLAG_CFG = 8 (8-warp backward) and 11 (16-warp backward) on shapes that would otherwise take the first generation:
+values against the fp64 C oracle.
 Tolerances (north_star): 1e-4 fp32 I/O, 2e-2 bf16 I/O (5e-3 fp16), max|a-b| / max|b|."""
 import numpy as np
 import pytest
@@ -11,6 +12,16 @@ from tests.util import relerr, scan_inputs
 
 pytestmark = pytest.mark.gpu
 V2 = 8 << 4
+
+
+@pytest.fixture(autouse=True, params=[8, 11], ids=["w8", "w16"])
+def _generation(request):
+    """every test of this module runs once per backward kernel (the flag also selects the forward: 8 = second generation,
+    11 = default dispatch)"""
+    globals()["V2"] = request.param << 4
+    yield
+    globals()["V2"] = 8 << 4
+
 TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2, torch.float16: 5e-3}
 
 
@@ -18,8 +29,9 @@ def _t(a, dtype=torch.float32):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda().to(dtype)
 
 
-def _run(inp, dtype=torch.float32, gate=True, flags=V2, softplus=False):
+def _run(inp, dtype=torch.float32, gate=True, flags=None, softplus=False):
     from mmidet_b200 import _lib, ops
+    flags = V2 if flags is None else flags
     if softplus:
         flags |= _lib.FLAG_DELTA_SOFTPLUS
     a = {k: _t(inp[k], torch.float32 if k in ("A", "D") else dtype) for k in ("x", "delta", "z", "A", "Bm", "Cm", "D", "dout")}
