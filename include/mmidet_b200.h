@@ -90,8 +90,9 @@ int mmi_selscan_bwd(const void *x, const void *delta, const void *z, const float
  *   A, X, H : (B, L, D, N) fp32 contiguous.  Inputs are not modified (reference clones, pscan.py:167-174).
  * mmi_pscan_bwd replaces PScan.backward (models/pscan.py:189-224): gA[t] = H[t-1]*G[t] (gA[0]=0), gX = G with
  *   G[t] = gH[t] + A[t+1]*G[t+1].
- * L is split into segments scanned in parallel; `ws` (>= mmi_pscan_ws_bytes bytes) holds the per-segment
- * (product, local state) summaries that the second pass chains.  Any D, N (only D*N matters).
+ * One pass over the tensors: L is cut into 32-step segments scanned in parallel and chained by a decoupled look-back;
+ * `ws` (>= mmi_pscan_ws_bytes bytes, contents arbitrary) holds the item ticket and the per-(segment, column) records
+ * {product, local end state, inclusive state, status}.  Results are bit-reproducible.  Any D, N (only D*N matters).
  * --------------------------------------------------------------------------------------------------------- */
 int64_t mmi_pscan_ws_bytes(int B, int L, int D, int N);
 int mmi_pscan_fwd(const float *A, const float *X, float *H, void *ws, int B, int L, int D, int N, void *stream);

@@ -27,9 +27,11 @@ def test_pscan_vs_reference_golden(golden, tag):
     assert torch.equal(A.detach(), A0) and torch.equal(X.detach(), X0)  # inputs untouched (pscan.py:167-170)
 
 
-@pytest.mark.parametrize("shape", [(2, 777, 32, 16), (1, 6400, 64, 16), (3, 65, 5, 3), (2, 1, 8, 16)])
+@pytest.mark.parametrize("shape", [(2, 777, 32, 16), (1, 6400, 64, 16), (3, 65, 5, 3), (2, 1, 8, 16), (1, 31, 9, 16), (2, 32, 8, 16),
+                                   (1, 33, 3, 16), (2, 2000, 9, 16), (64, 200, 4, 16)])
 def test_pscan_vs_oracle_multi_segment(shape):
-    """non-pow2 L long enough to be cut into several segments; odd D*N."""
+    """non-pow2 L cut into many 32-step segments (look-back chains of up to 200 records), L around the segment length, D*N
+    below / not a multiple of the 128 columns of a CTA, more (batch, column block) chains than resident CTAs."""
     from mmidet_b200.pscan import pscan
     rng = np.random.default_rng(1)
     A = (rng.random(shape) * 0.5 + 0.5).astype(np.float32)
@@ -43,6 +45,25 @@ def test_pscan_vs_oracle_multi_segment(shape):
     assert relerr(H.detach().cpu().numpy(), H64) <= 1e-4
     assert relerr(gA.cpu().numpy(), gA64) <= 1e-4
     assert relerr(gX.cpu().numpy(), gX64) <= 1e-4
+
+
+def test_pscan_is_bit_reproducible():
+    """the look-back chains the parked aggregates oldest first, so the value does not depend on how deep each thread had to
+    look: repeated runs give identical bits, forward and backward."""
+    from mmidet_b200.pscan import pscan
+    rng = np.random.default_rng(4)
+    shape = (2, 3000, 40, 16)
+    A = _t((rng.random(shape) * 0.5 + 0.5).astype(np.float32)).requires_grad_(True)
+    X = _t(rng.standard_normal(shape).astype(np.float32)).requires_grad_(True)
+    gH = _t(rng.standard_normal(shape).astype(np.float32))
+    runs = []
+    for _ in range(4):
+        H = pscan(A, X)
+        gA, gX = torch.autograd.grad(H, (A, X), gH)
+        runs.append((H.detach().clone(), gA.clone(), gX.clone()))
+    for r in runs[1:]:
+        for u, v in zip(runs[0], r):
+            assert torch.equal(u, v)
 
 
 def test_pscan_fp64_vs_reference_golden(golden):
