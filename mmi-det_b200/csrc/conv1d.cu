@@ -72,53 +72,80 @@ struct ConvParams {
     int64_t x_ld, y_ld, dy_ld, dx_ld;
 };
 
+// The arithmetic runs on packed pairs (FFMA2 / FMUL2 / FADD2): a thread's 4 channels are two float2 lanes.  At 6 bytes per
+// element and direction (16-bit I/O) the scalar form of these kernels was bound by instruction issue, not by HBM.
+struct F4 {
+    float2 lo, hi;  // channels (c, c+1) | (c+2, c+3)
+};
+__device__ __forceinline__ F4 f4_zero() { return {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}; }
+__device__ __forceinline__ F4 f4_from(const float (&v)[4]) { return {make_float2(v[0], v[1]), make_float2(v[2], v[3])}; }
+__device__ __forceinline__ F4 f4_fma(const F4 &a, const F4 &b, const F4 &c) { return {fma2(a.lo, b.lo, c.lo), fma2(a.hi, b.hi, c.hi)}; }
+__device__ __forceinline__ F4 f4_mul(const F4 &a, const F4 &b) { return {mul2(a.lo, b.lo), mul2(a.hi, b.hi)}; }
+__device__ __forceinline__ F4 f4_add(const F4 &a, const F4 &b) { return {add2(a.lo, b.lo), add2(a.hi, b.hi)}; }
+__device__ __forceinline__ float2 sigmoid2(float2 z) {
+    const float2 e = mul2(z, splat2(-kLog2e));
+    const float2 d = add2(make_float2(ex2(e.x), ex2(e.y)), splat2(1.f));
+    return make_float2(rcp(d.x), rcp(d.y));
+}
+__device__ __forceinline__ F4 f4_sigmoid(const F4 &z) { return {sigmoid2(z.lo), sigmoid2(z.hi)}; }
+template <typename T> __device__ __forceinline__ F4 f4_unpack(const typename Vec4<T>::raw &q) {
+    float v[4];
+    Vec4<T>::unpack(q, v);
+    return f4_from(v);
+}
+template <typename T> __device__ __forceinline__ void f4_store(T *p, const F4 &o) {
+    const float v[4] = {o.lo.x, o.lo.y, o.hi.x, o.hi.y};
+    Vec4<T>::store(p, v);
+}
+
 // grid (ceil(ED / 128), ceil(L / (kConvSeg * kConvWarps)), B); block 32 x kConvWarps
 template <typename T, int K> __global__ void __launch_bounds__(32 * kConvWarps) causal_conv1d_fwd_kernel(const ConvParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = (blockIdx.x * 32 + lane) * 4, b = blockIdx.z;
     const int t0 = (blockIdx.y * kConvWarps + warp) * kConvSeg;
     if (c >= p.ED || t0 >= p.L) return;
-    float w[K][4], bs[4];
+    F4 w[K], bs;
+    {
+        float bv[4], wv[K][4];
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-        bs[v] = p.bias ? p.bias[c + v] : 0.f;
+        for (int v = 0; v < 4; ++v) {
+            bv[v] = p.bias ? p.bias[c + v] : 0.f;
 #pragma unroll
-        for (int j = 0; j < K; ++j) w[j][v] = p.w[(c + v) * K + j];
+            for (int j = 0; j < K; ++j) wv[j][v] = p.w[(c + v) * K + j];
+        }
+        bs = f4_from(bv);
+#pragma unroll
+        for (int j = 0; j < K; ++j) w[j] = f4_from(wv[j]);
     }
     const T *x = static_cast<const T *>(p.x) + int64_t(b) * p.L * p.x_ld + c;
     T *y = static_cast<T *>(p.y) + int64_t(b) * p.L * p.y_ld + c;
     // x of the last four steps lives in a ring indexed by (t - t0) & 3; the step loop is unrolled in multiples of four,
     // so every ring index is a compile-time constant and nothing is shifted between steps
-    float ring[4][4];
+    F4 ring[4];
 #pragma unroll
     for (int m = 1; m < K; ++m) {
         const int t = t0 - m;
-        if (t >= 0) Vec4<T>::load(x + int64_t(t) * p.x_ld, ring[(4 - m) & 3]);
-        else
-#pragma unroll
-            for (int v = 0; v < 4; ++v) ring[(4 - m) & 3][v] = 0.f;
+        ring[(4 - m) & 3] = t >= 0 ? f4_unpack<T>(Vec4<T>::ldraw(x + int64_t(t) * p.x_ld)) : f4_zero();
     }
     const int t1 = min(t0 + kConvSeg, p.L);
     constexpr int PB = sizeof(T) == 2 ? 8 : 4;  // rows requested ahead of their use (packed), see the backward kernel
-    for (int tb = t0; tb < t1; tb += PB) {
+    const T *xr = x + int64_t(t0) * p.x_ld;
+    T *yr = y + int64_t(t0) * p.y_ld;
+    for (int tb = t0; tb < t1; tb += PB, xr += PB * p.x_ld, yr += PB * p.y_ld) {
         typename Vec4<T>::raw xq[PB];
+        const bool whole = tb + PB <= t1;  // warp-uniform
 #pragma unroll
         for (int u = 0; u < PB; ++u)
-            if (tb + u < t1) xq[u] = Vec4<T>::ldraw(x + int64_t(tb + u) * p.x_ld);
+            if (whole || tb + u < t1) xq[u] = Vec4<T>::ldraw(xr + u * p.x_ld);
 #pragma unroll
         for (int u = 0; u < PB; ++u) {
-            const int t = tb + u;
-            if (t < t1) {
-                Vec4<T>::unpack(xq[u], ring[u & 3]);
-                float o[4];
+            if (whole || tb + u < t1) {
+                ring[u & 3] = f4_unpack<T>(xq[u]);
+                F4 acc = bs;
 #pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    float acc = bs[v];
-#pragma unroll
-                    for (int j = 0; j < K; ++j) acc = fmaf(w[j][v], ring[(u - (K - 1) + j) & 3][v], acc);  // x[t-(K-1)+j]
-                    o[v] = p.silu ? acc * sigmoidf_fast(acc) : acc;
-                }
-                Vec4<T>::store(y + int64_t(t) * p.y_ld, o);
+                for (int j = 0; j < K; ++j) acc = f4_fma(w[j], ring[(u - (K - 1) + j) & 3], acc);  // x[t-(K-1)+j]
+                if (p.silu) acc = f4_mul(acc, f4_sigmoid(acc));
+                f4_store<T>(yr + u * p.y_ld, acc);
             }
         }
     }
@@ -130,20 +157,22 @@ template <typename T, int K> __global__ void __launch_bounds__(32 * kConvWarps) 
     const int c = (blockIdx.x * 32 + lane) * 4, b = blockIdx.z;
     const int t0 = (blockIdx.y * kConvWarps + warp) * kConvSeg;
     const bool live = c < p.ED && t0 < p.L;
-    float dwa[K][4], dba[4];
+    F4 dwa[K], dba = f4_zero();
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-        dba[v] = 0.f;
-#pragma unroll
-        for (int j = 0; j < K; ++j) dwa[j][v] = 0.f;
-    }
+    for (int j = 0; j < K; ++j) dwa[j] = f4_zero();
     if (live) {
-        float w[K][4], bs[4];
+        F4 w[K], bs;
+        {
+            float bv[4], wv[K][4];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            bs[v] = p.bias ? p.bias[c + v] : 0.f;
+            for (int v = 0; v < 4; ++v) {
+                bv[v] = p.bias ? p.bias[c + v] : 0.f;
 #pragma unroll
-            for (int j = 0; j < K; ++j) w[j][v] = p.w[(c + v) * K + j];
+                for (int j = 0; j < K; ++j) wv[j][v] = p.w[(c + v) * K + j];
+            }
+            bs = f4_from(bv);
+#pragma unroll
+            for (int j = 0; j < K; ++j) w[j] = f4_from(wv[j]);
         }
         const T *x = static_cast<const T *>(p.x) + int64_t(b) * p.L * p.x_ld + c;
         const T *dy = static_cast<const T *>(p.dy) + int64_t(b) * p.L * p.dy_ld + c;
@@ -151,68 +180,60 @@ template <typename T, int K> __global__ void __launch_bounds__(32 * kConvWarps) 
         // walk t = t0 .. t1 + K - 2: dpre[t] needs x[t-K+1 .. t]; dx[s] (s = t - K + 1) needs dpre[s .. s+K-1]
         // x and dpre of the last four steps live in rings indexed by (t - t0) & 3 (compile-time constants after unrolling
         // in multiples of four: no register shifting between steps)
-        float xr[4][4], dr[4][4];
+        F4 xr[4], dr[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int v = 0; v < 4; ++v) xr[j][v] = dr[j][v] = 0.f;
+        for (int j = 0; j < 4; ++j) xr[j] = dr[j] = f4_zero();
 #pragma unroll
         for (int m = 1; m < K; ++m) {
             const int t = t0 - m;
-            if (t >= 0) Vec4<T>::load(x + int64_t(t) * p.x_ld, xr[(4 - m) & 3]);
+            if (t >= 0) xr[(4 - m) & 3] = f4_unpack<T>(Vec4<T>::ldraw(x + int64_t(t) * p.x_ld));
         }
         const int t1 = min(t0 + kConvSeg, p.L), tend = t1 + K - 1;
         // the walk is serial per thread: the x / dy rows of the next PB steps are requested (packed) before the first of
         // them is used, otherwise every step waits out a full memory latency
         constexpr int PB = sizeof(T) == 2 ? 8 : 4;
-        for (int tb = t0; tb < tend; tb += PB) {
+        const T *xp = x + int64_t(t0) * p.x_ld, *gp = dy + int64_t(t0) * p.dy_ld;
+        T *op = dx + int64_t(t0 - (K - 1)) * p.dx_ld;  // row of dx written at step t: t - (K - 1)
+        for (int tb = t0; tb < tend; tb += PB, xp += PB * p.x_ld, gp += PB * p.dy_ld, op += PB * p.dx_ld) {
             typename Vec4<T>::raw xq[PB], gq[PB];
+            // warp-uniform fast path: all PB steps are inside the thread's own segment and inside L, and (past the first
+            // block) every dx row they complete belongs to the segment -- no per-step predicates
+            const bool whole = tb + PB <= t1 && tb > t0;
 #pragma unroll
             for (int u = 0; u < PB; ++u)
-                if (tb + u < tend && tb + u < p.L) {
-                    xq[u] = Vec4<T>::ldraw(x + int64_t(tb + u) * p.x_ld);
-                    gq[u] = Vec4<T>::ldraw(dy + int64_t(tb + u) * p.dy_ld);
+                if (whole || (tb + u < tend && tb + u < p.L)) {
+                    xq[u] = Vec4<T>::ldraw(xp + u * p.x_ld);
+                    gq[u] = Vec4<T>::ldraw(gp + u * p.dy_ld);
                 }
 #pragma unroll
             for (int u = 0; u < PB; ++u) {
                 const int t = tb + u;
-                if (t < tend) {
-                    if (t < p.L) {
-                        float g[4];
-                        Vec4<T>::unpack(xq[u], xr[u & 3]);
-                        Vec4<T>::unpack(gq[u], g);
+                if (whole || t < tend) {
+                    if (whole || t < p.L) {
+                        xr[u & 3] = f4_unpack<T>(xq[u]);
+                        F4 pre = bs;
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) {
-                            float pre = bs[v];
+                        for (int j = 0; j < K; ++j) pre = f4_fma(w[j], xr[(u - (K - 1) + j) & 3], pre);
+                        F4 d = f4_unpack<T>(gq[u]);
+                        if (p.silu) {  // d silu(pre) / d pre = sg (1 + pre (1 - sg))
+                            const F4 sg = f4_sigmoid(pre);
+                            const F4 one = {splat2(1.f), splat2(1.f)}, om = {add2(splat2(1.f), mul2(sg.lo, splat2(-1.f))), add2(splat2(1.f), mul2(sg.hi, splat2(-1.f)))};
+                            d = f4_mul(d, f4_mul(sg, f4_fma(pre, om, one)));
+                        }
+                        dr[u & 3] = d;
+                        if (whole || t < t1) {  // parameter gradients: own segment only (halo steps belong to the next segment)
+                            dba = f4_add(dba, d);
 #pragma unroll
-                            for (int j = 0; j < K; ++j) pre = fmaf(w[j][v], xr[(u - (K - 1) + j) & 3][v], pre);
-                            float d = g[v];
-                            if (p.silu) {
-                                const float sg = sigmoidf_fast(pre);
-                                d *= sg * fmaf(pre, 1.f - sg, 1.f);
-                            }
-                            dr[u & 3][v] = d;
-                            if (t < t1) {  // parameter gradients: own segment only (halo steps belong to the next segment)
-                                dba[v] += d;
-#pragma unroll
-                                for (int j = 0; j < K; ++j) dwa[j][v] = fmaf(d, xr[(u - (K - 1) + j) & 3][v], dwa[j][v]);
-                            }
+                            for (int j = 0; j < K; ++j) dwa[j] = f4_fma(d, xr[(u - (K - 1) + j) & 3], dwa[j]);
                         }
                     } else {
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) xr[u & 3][v] = dr[u & 3][v] = 0.f;
+                        xr[u & 3] = dr[u & 3] = f4_zero();
                     }
-                    const int sx = t - (K - 1);
-                    if (sx >= t0) {  // dx[s] = sum_j w[j] * dpre[s + K-1 - j] = sum_j w[j] * dpre[t - j]
-                        float o[4];
+                    if (whole || t - (K - 1) >= t0) {  // dx[s] = sum_j w[j] * dpre[s + K-1 - j] = sum_j w[j] * dpre[t - j]
+                        F4 acc = f4_mul(w[0], dr[u & 3]);
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) {
-                            float acc = 0.f;
-#pragma unroll
-                            for (int j = 0; j < K; ++j) acc = fmaf(w[j][v], dr[(u - j) & 3][v], acc);
-                            o[v] = acc;
-                        }
-                        Vec4<T>::store(dx + int64_t(sx) * p.dx_ld, o);
+                        for (int j = 1; j < K; ++j) acc = f4_fma(w[j], dr[(u - j) & 3], acc);
+                        f4_store<T>(op + u * p.dx_ld, acc);
                     }
                 }
             }
@@ -220,11 +241,8 @@ template <typename T, int K> __global__ void __launch_bounds__(32 * kConvWarps) 
     }
     // block reduction over the kConvWarps time segments, then one atomic per (channel, tap)
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-#pragma unroll
-        for (int j = 0; j < K; ++j) red[warp][j][lane * 4 + v] = dwa[j][v];
-        red[warp][K][lane * 4 + v] = dba[v];
-    }
+    for (int j = 0; j < K; ++j) *reinterpret_cast<float4 *>(&red[warp][j][lane * 4]) = make_float4(dwa[j].lo.x, dwa[j].lo.y, dwa[j].hi.x, dwa[j].hi.y);
+    *reinterpret_cast<float4 *>(&red[warp][K][lane * 4]) = make_float4(dba.lo.x, dba.lo.y, dba.hi.x, dba.hi.y);
     __syncthreads();
     for (int i = threadIdx.x; i < (K + 1) * 128; i += 32 * kConvWarps) {
         const int j = i / 128, cc = i % 128, ch = blockIdx.x * 128 + cc;

@@ -90,7 +90,15 @@ int mmi_selscan_fwd_bwd_host(const void *x, const void *delta, const void *z, co
     // The batch is cut into chunks that flow through a 3-stage pipeline on three streams -- H2D of chunk i+1, forward +
     // backward of chunk i and D2H of chunk i-1 run concurrently (PCIe is full duplex) -- over two device staging slots.
     const size_t es = dtype == MMI_F32 ? 4 : 2;
-    const int nchunk = B < 8 ? B : 8, cb = (B + nchunk - 1) / nchunk;
+    // 8 chunks by default (MMI_HOST_CHUNKS overrides, 1..64): fill and drain of the pipeline cost 2 / (nchunk + 2) of the step,
+    // smaller chunks cost kernel efficiency and per-copy overhead -- measured at B=16 L=6400 ED=512 fp32: 4 / 6 / 8 / 12 / 16
+    // chunks = 25.0 / 22.1 / 22.8 / 21.8 / 23.5 ms per step, i.e. PCIe-bound and flat (profiles/r02_scan_generations.txt)
+    static const int want = [] {
+        const char *e = getenv("MMI_HOST_CHUNKS");
+        const int v = e ? atoi(e) : 8;
+        return v < 1 ? 1 : (v > 64 ? 64 : v);
+    }();
+    const int nchunk = B < want ? B : want, cb = (B + nchunk - 1) / nchunk;
     const size_t big = al(size_t(cb) * L * ED * es), bc = al(size_t(cb) * L * N * es), an = al(size_t(ED) * N * 4), dn = al(size_t(ED) * 4);
     const int nchk = (L + kChunk - 1) / kChunk;
     const size_t chkb = al(size_t(cb) * nchk * ED * N * 4), wsb = al(size_t(mmi_selscan_bwd_ws_bytes(cb, L, ED, N)));

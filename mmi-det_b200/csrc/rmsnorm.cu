@@ -4,7 +4,7 @@
 // stock PyTorch) evaluates as five elementwise / reduction kernels per direction.  HBM-bound: the forward reads x and
 // writes y once (the row stays in registers between the reduction and the scaling); the backward reads x and dy once,
 //     dx = r * (w*dy - x * r^2 * mean(w*dy*x)),   r = rsqrt(mean(x^2) + eps),   dw = sum_rows dy * x * r,
-// with dw accumulated per warp over a strip of rows and finished with one fp32 atomic per (warp, channel).
+// with dw accumulated per lane over a strip of rows and finished with one fp32 atomic per (block, channel).
 #include "../../include/mmidet_b200.h"
 #include "common.cuh"
 
@@ -105,99 +105,105 @@ __global__ void __launch_bounds__(128) rmsnorm_fwd_kernel(const T *__restrict__ 
     }
 }
 
-template <typename T, typename TY, int NV>
+// Backward, rows up to 1024 channels.  A row is owned by a group of LPR = 8 / 16 / 32 lanes (C <= 256 / 512 / 1024), so a warp
+// works on 32 / LPR rows at once: the two row reductions (sum x^2, sum w dy x) take log2(LPR) shuffle rounds for ALL of the
+// warp's rows together instead of five rounds per row, the arithmetic runs on packed pairs (FFMA2 / FMUL2), and a lane keeps
+// its <= 32 channels of w and of the dw accumulator in registers over the whole strip of rows.  NCH = chunks of 4 channels per
+// lane; chunk i of sub-lane s covers channels (i * LPR + s) * 4 (coalesced across the group).
+template <typename T, typename TY, int LPR, int NCH>
 __global__ void __launch_bounds__(128) rmsnorm_bwd_kernel(const T *__restrict__ x, const float *__restrict__ w, const TY *__restrict__ dy,
                                                           T *__restrict__ dx, float *__restrict__ dw, int64_t rows, int C, int64_t x_ld,
                                                           int64_t dy_ld, int64_t dx_ld, float eps) {
-    const int lane = threadIdx.x & 31;
-    const int64_t row0 = (int64_t(blockIdx.x) * 4 + (threadIdx.x >> 5)) * kRmsRowsPerWarp;
-    float wv[NV][4], dwa[NV][4];
+    constexpr int RW = 32 / LPR;  // rows per warp step
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % LPR, rw = lane / LPR;
+    const int64_t row0 = (int64_t(blockIdx.x) * 4 + warp) * kRmsRowsPerWarp;
+    float2 wv[NCH][2], dwa[NCH][2];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const int c = (i * 32 + lane) * 4;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) dwa[i][k] = 0.f;
+    for (int i = 0; i < NCH; ++i) {
+        const int c = (i * LPR + sub) * 4;
+        dwa[i][0] = dwa[i][1] = make_float2(0.f, 0.f);
+        wv[i][0] = wv[i][1] = make_float2(0.f, 0.f);
         if (c < C) {
             const float4 ww = __ldg(reinterpret_cast<const float4 *>(w + c));
-            wv[i][0] = ww.x; wv[i][1] = ww.y; wv[i][2] = ww.z; wv[i][3] = ww.w;
+            wv[i][0] = make_float2(ww.x, ww.y), wv[i][1] = make_float2(ww.z, ww.w);
         }
     }
-    // Rows are independent but a warp walks its strip serially, and registers cap the resident warps (6 blocks per SM at
-    // NV = 2): bytes in flight = warps x rows in flight x row bytes.  Rows are therefore requested RB at a time, packed,
-    // before the first of them is reduced (one row at a time left 16-bit maps latency-bound at a third of the HBM peak).
     using Raw = typename RmsRaw<T>::type;
     using RawY = typename RmsRaw<TY>::type;
-    constexpr int RB = NV <= 2 ? 4 : (NV == 4 ? 2 : 1);
-    const int nrow = int(min(int64_t(kRmsRowsPerWarp), rows - row0));
-    for (int r0 = 0; r0 < nrow; r0 += RB) {
-        Raw xq[RB][NV];
-        RawY gq[RB][NV];
+    const float invC = 1.f / float(C);
+    for (int r0 = 0; r0 < kRmsRowsPerWarp; r0 += RW) {
+        const int64_t row = row0 + r0 + rw;
+        const bool live = row < rows;
+        if (row0 + r0 >= rows) break;  // warp-uniform
+        Raw xq[NCH];
+        RawY gq[NCH];
 #pragma unroll
-        for (int b = 0; b < RB; ++b)
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const int c = (i * 32 + lane) * 4;
-                if (r0 + b < nrow && c < C) {
-                    xq[b][i] = rms_ldraw<T>(x + (row0 + r0 + b) * x_ld + c);
-                    gq[b][i] = rms_ldraw<TY>(dy + (row0 + r0 + b) * dy_ld + c);
-                }
+        for (int i = 0; i < NCH; ++i) {
+            const int c = (i * LPR + sub) * 4;
+            if (live && c < C) {
+                xq[i] = rms_ldraw<T>(x + row * x_ld + c);
+                gq[i] = rms_ldraw<TY>(dy + row * dy_ld + c);
             }
+        }
+        float2 xv[NCH][2], gw[NCH][2], gv[NCH][2];
+        float2 ss2 = make_float2(0.f, 0.f), sg2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int b = 0; b < RB; ++b) {
-            if (r0 + b >= nrow) break;
-            const int64_t row = row0 + r0 + b;
-            float xv[NV][4], gv[NV][4];
-            float ss = 0.f, sg = 0.f;
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const int c = (i * 32 + lane) * 4;
-                if (c < C) {
-                    rms_unpack<T>(xq[b][i], xv[i]);
-                    rms_unpack<TY>(gq[b][i], gv[i]);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        ss = fmaf(xv[i][k], xv[i][k], ss);
-                        sg = fmaf(gv[i][k] * wv[i][k], xv[i][k], sg);
-                    }
-                }
+        for (int i = 0; i < NCH; ++i) {
+            const int c = (i * LPR + sub) * 4;
+            float a[4] = {0.f, 0.f, 0.f, 0.f}, g[4] = {0.f, 0.f, 0.f, 0.f};
+            if (live && c < C) {
+                rms_unpack<T>(xq[i], a);
+                rms_unpack<TY>(gq[i], g);
             }
-            ss = warp_sum(ss);
-            sg = warp_sum(sg);
-            const float r = rsqrtf(ss / float(C) + eps);
-            const float coef = r * r * r * sg / float(C);
+            xv[i][0] = make_float2(a[0], a[1]), xv[i][1] = make_float2(a[2], a[3]);
+            gv[i][0] = make_float2(g[0], g[1]), gv[i][1] = make_float2(g[2], g[3]);
 #pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const int c = (i * 32 + lane) * 4;
-                if (c < C) {
-                    float o[4];
+            for (int h = 0; h < 2; ++h) {
+                gw[i][h] = mul2(gv[i][h], wv[i][h]);
+                ss2 = fma2(xv[i][h], xv[i][h], ss2);
+                sg2 = fma2(gw[i][h], xv[i][h], sg2);
+            }
+        }
+        float ss = ss2.x + ss2.y, sg = sg2.x + sg2.y;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        o[k] = fmaf(gv[i][k] * wv[i][k], r, -xv[i][k] * coef);
-                        dwa[i][k] = fmaf(gv[i][k] * r, xv[i][k], dwa[i][k]);
-                    }
-                    rms_store4<T>(dx + row * dx_ld + c, o);
-                }
+        for (int m = LPR / 2; m >= 1; m >>= 1) {  // within the row's lane group; all rows of the warp at once
+            ss += __shfl_xor_sync(0xffffffffu, ss, m);
+            sg += __shfl_xor_sync(0xffffffffu, sg, m);
+        }
+        const float r = rsqrtf(ss * invC + eps);
+        const float2 r2 = splat2(r), ncoef = splat2(-(r * r * r * sg * invC));
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+            const int c = (i * LPR + sub) * 4;
+            float2 o[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                o[h] = fma2(xv[i][h], ncoef, mul2(gw[i][h], r2));                 // r w dy - x r^3 mean(w dy x)
+                dwa[i][h] = fma2(mul2(gv[i][h], r2), xv[i][h], dwa[i][h]);        // dw += dy x r
+            }
+            if (live && c < C) {
+                const float ov[4] = {o[0].x, o[0].y, o[1].x, o[1].y};
+                rms_store4<T>(dx + row * dx_ld + c, ov);
             }
         }
     }
-    __shared__ float red[3][NV * 128];
-    const int warp = threadIdx.x >> 5;
+    // dw: sum over the warp's row groups and the block's four warps in shared memory, one atomic per channel and block
+    __shared__ float4 red[4][RW][NCH * LPR];
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
-        if (warp > 0)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) red[warp - 1][(i * 32 + lane) * 4 + k] = dwa[i][k];
+    for (int i = 0; i < NCH; ++i) red[warp][rw][i * LPR + sub] = make_float4(dwa[i][0].x, dwa[i][0].y, dwa[i][1].x, dwa[i][1].y);
     __syncthreads();
-    if (warp == 0) {
+    for (int q = threadIdx.x; q < NCH * LPR; q += 128) {
+        const int c = q * 4;
+        if (c >= C) continue;
+        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int c = (i * 32 + lane) * 4;
-            if (c < C) {
+        for (int wq = 0; wq < 4; ++wq)
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    atomicAdd(dw + c + k, dwa[i][k] + red[0][c + k] + red[1][c + k] + red[2][c + k]);
+            for (int g = 0; g < RW; ++g) {
+                const float4 v = red[wq][g][q];
+                s4.x += v.x, s4.y += v.y, s4.z += v.z, s4.w += v.w;
             }
-        }
+        atomicAdd(dw + c, s4.x), atomicAdd(dw + c + 1, s4.y), atomicAdd(dw + c + 2, s4.z), atomicAdd(dw + c + 3, s4.w);
     }
 }
 
@@ -319,12 +325,8 @@ template <typename T, typename TY> static int rms_launch_t(bool bwd, const void 
         if (int e = check_cuda(cudaMemsetAsync(dw, 0, size_t(C) * 4, st), "rmsnorm dw memset")) return e;
     const unsigned gf = unsigned((rows + 3) / 4), gb = unsigned((rows + 4 * kRmsRowsPerWarp - 1) / (4 * kRmsRowsPerWarp));
 #define MMI_RMS(NVV)                                                                                                   \
-    if (C <= 128 * NVV) {                                                                                              \
-        if (bwd)                                                                                                       \
-            rmsnorm_bwd_kernel<T, TY, NVV><<<gb, 128, 0, st>>>(xp, w, static_cast<const TY *>(dy), static_cast<T *>(out), dw, rows, C, \
-                                                               x_ld, dy_ld, out_ld, eps);                              \
-        else                                                                                                           \
-            rmsnorm_fwd_kernel<T, TY, NVV><<<gf, 128, 0, st>>>(xp, w, static_cast<TY *>(out), nullptr, rows, C, x_ld, out_ld, eps); \
+    if (!bwd && C <= 128 * NVV) {                                                                                      \
+        rmsnorm_fwd_kernel<T, TY, NVV><<<gf, 128, 0, st>>>(xp, w, static_cast<TY *>(out), nullptr, rows, C, x_ld, out_ld, eps); \
         return check_cuda(cudaGetLastError(), "rmsnorm launch");                                                      \
     }
     MMI_RMS(1)
@@ -332,6 +334,18 @@ template <typename T, typename TY> static int rms_launch_t(bool bwd, const void 
     MMI_RMS(4)
     MMI_RMS(8)
 #undef MMI_RMS
+#define MMI_RMS_B(LPR, NCH)                                                                                            \
+    if (bwd && C <= 4 * LPR * NCH) {                                                                                   \
+        rmsnorm_bwd_kernel<T, TY, LPR, NCH><<<gb, 128, 0, st>>>(xp, w, static_cast<const TY *>(dy), static_cast<T *>(out), dw, rows, C, \
+                                                                x_ld, dy_ld, out_ld, eps);                             \
+        return check_cuda(cudaGetLastError(), "rmsnorm backward launch");                                             \
+    }
+    MMI_RMS_B(8, 2)   // C <= 64
+    MMI_RMS_B(8, 4)   // C <= 128
+    MMI_RMS_B(8, 8)   // C <= 256
+    MMI_RMS_B(16, 8)  // C <= 512
+    MMI_RMS_B(32, 8)  // C <= 1024
+#undef MMI_RMS_B
 #define MMI_RMS_WIDE(NVV)                                                                                              \
     if (C <= kRmsWideThreads * 4 * NVV) {                                                                              \
         if (bwd)                                                                                                       \
