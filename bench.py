@@ -23,7 +23,7 @@ need the reference detector, which does not travel to the GPU box; they are pari
   general_A / bf16   the same step with a trained (non-geometric) A, and with bf16 I/O: what a training run sees after the
             first optimizer step / under autocast (secondary legs, a few steps each).
   train     BASELINE configs[3]: the data-parallel training step of the UNMODIFIED reference detector (two-stream
-            YOLOv5l, 16 synthetic pairs per GPU, bf16 autocast, ComputeLoss, SGD) with the CUDA fusion path plugged in,
+            YOLOv5l, 16 synthetic pairs per GPU, fp16 autocast + GradScaler as in train.py, ComputeLoss, SGD) with the CUDA fusion path plugged in,
             DDP gradient all-reduce over NCCL overlapped with the backward (8 MB buckets); `exposed_allreduce_ms` is the
             step time minus the same step under no_sync().  Needs the staged reference (baseline/_ref).
 Only this file's cpu legs and tests/ touch oracle/; the product path is the CUDA library and fails loudly
@@ -271,6 +271,7 @@ def detector_train_leg(rank, world, local_rank, dist, steps=8, warmup=5):
         net = DDP(model, device_ids=[local_rank], output_device=local_rank, bucket_cap_mb=8, gradient_as_bucket_view=True,
                   broadcast_buffers=False)
     imgs, targets = H.synthetic_batch(B, imgsz, seed=100 + rank)
+    scaler = H.make_scaler(torch.float16)  # the reference's recipe: fp16 autocast + GradScaler (train.py:706, :784-801)
 
     def run(n, sync=True):
         # sync=False: the same step on the bare module (no DDP hooks, no all-reduce) -- what this rank would do alone.
@@ -283,7 +284,7 @@ def detector_train_leg(rank, world, local_rank, dist, steps=8, warmup=5):
         torch.cuda.synchronize()
         e0.record()
         for _ in range(n):
-            loss = H.train_step(target, compute_loss, opt, imgs, targets, autocast_dtype=torch.bfloat16, world_size=world)
+            loss = H.train_step(target, compute_loss, opt, imgs, targets, autocast_dtype=torch.float16, world_size=world, scaler=scaler)
         e1.record()
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1) / n], device="cuda", dtype=torch.float64)
@@ -294,7 +295,7 @@ def detector_train_leg(rank, world, local_rank, dist, steps=8, warmup=5):
     run(warmup)
     ms, loss = run(steps)
     leg = {"config": "two-stream YOLOv5l (unmodified reference Model / ComputeLoss, fusion = MambaFusion on the sm_100a kernels), "
-                     "640x640 synthetic pairs, 16 / GPU, bf16 autocast, SGD, channels_last backbone",
+                     "640x640 synthetic pairs, 16 / GPU, fp16 autocast + GradScaler (train.py:784-801), SGD, channels_last backbone",
            "pairs_per_s": round(world * B / (ms * 1e-3), 2), "ms_per_step": round(ms, 3), "n_gpus": world, "steps": steps,
            "params": nparam, "allreduce_bytes_per_step": nparam * 4 if world > 1 else 0, "loss": round(loss, 5)}
     if world > 1:

@@ -11,7 +11,7 @@ the reference's own drivers do inline:
     synthetic_batch / prep_inputs     train.py:741-745 (uint8 batch -> float / 255 -> RGB | IR split), SURVEY 8d config 4
     make_optimizer / scale_hyp        train.py:567-587, :688-696 (SGD groups by module attribute; bare Parameters such as
                                       A_log / D land in no group, SURVEY App. B -- kept, it is the reference's behaviour)
-    train_step                        train.py:783-804 (autocast forward, ComputeLoss, backward, optimizer step)
+    train_step / make_scaler          train.py:783-804, :706 (fp16 autocast forward, ComputeLoss, scaled backward, optimizer step)
     infer                             detect_twostream.py:88-94 (model forward + non_max_suppression timing window)
     load_checkpoint                   models/experimental.py:113-134 (attempt_load) for the checkpoints train.py:882-894 writes
     quiet()                           the per-step print()/sync points of utils/loss.py:162-182 and
@@ -221,9 +221,17 @@ def prep_inputs(imgs_u8: torch.Tensor, dtype=torch.float32):
     return postprocess.split_normalize(imgs_u8, dtype)
 
 
-def train_step(model, compute_loss, optimizer, imgs_u8, targets, autocast_dtype=torch.bfloat16, world_size: int = 1,
-               fused_prep: bool = True):
-    """train.py:783-804 for one batch.  Returns the (device) loss tensor; no host sync inside."""
+def make_scaler(autocast_dtype=torch.float16):
+    """train.py:706: `amp.GradScaler(enabled=cuda)` -- the reference trains under fp16 autocast with loss scaling.  Returns None
+    for the precisions that need no scaling (bf16 autocast, fp32)."""
+    return torch.amp.GradScaler("cuda") if autocast_dtype == torch.float16 else None
+
+
+def train_step(model, compute_loss, optimizer, imgs_u8, targets, autocast_dtype=torch.float16, world_size: int = 1,
+               fused_prep: bool = True, scaler=None):
+    """train.py:783-804 for one batch: autocast forward (fp16 in the reference, :784), ComputeLoss, `scaler.scale(loss).backward()`
+    (:796), `scaler.step(optimizer)` / `scaler.update()` (:800-801; with scaler=None a plain backward / step).  Returns the
+    (device) loss tensor; no host sync inside."""
     if fused_prep:
         rgb, ir = prep_inputs(imgs_u8)
     else:  # the reference's three elementwise / copy passes
@@ -234,8 +242,13 @@ def train_step(model, compute_loss, optimizer, imgs_u8, targets, autocast_dtype=
         loss, _ = compute_loss(pred, targets, comb.reshape(-1))  # a 0-d Combine_loss breaks len()
         if world_size > 1:
             loss = loss * world_size  # train.py:790-791
-    loss.backward()
-    optimizer.step()
+    if scaler is not None:
+        scaler.scale(loss).backward()
+        scaler.step(optimizer)
+        scaler.update()
+    else:
+        loss.backward()
+        optimizer.step()
     optimizer.zero_grad(set_to_none=True)
     return loss.detach()
 

@@ -5,7 +5,7 @@
         two-stream YOLOv5s forward, batch 1: Detect output of the CUDA fusion path vs the same model on the reference's
         pure-PyTorch MambaBlock / pscan, both on the GPU, same weights -> rel-err + latency of both arms        (configs[1])
     python [-m torch.distributed.run ...] scripts/detector_bench.py train [--size l] [--batch 16] [--arm ours|pytorch]
-        training step (uint8 batch -> /255 -> split, autocast bf16 forward, ComputeLoss, backward, DDP gradient
+        training step (uint8 batch -> /255 -> split, fp16 autocast forward + GradScaler as train.py:784-801, ComputeLoss, backward, DDP gradient
         all-reduce, SGD step), 16 pairs / GPU, torchrun at 1/2/4/8 -> image-pairs / s                              (configs[3])
     python scripts/detector_bench.py infer [--size x] [--imgsz 1280] [--batch 32]
         detect_twostream.py's timing window (model forward + NMS), fp16 -> pairs / s, p50 / p99 latency           (configs[4])
@@ -88,9 +88,11 @@ def mode_train(args):
     imgs, targets = H.synthetic_batch(args.batch, args.imgsz, seed=100 + rank)
     ac = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": None}[args.autocast]
 
+    scaler = H.make_scaler(ac)  # fp16: the reference's GradScaler (train.py:706, :796-801)
+
     def step():
         return H.train_step(net, compute_loss, opt, imgs, targets, autocast_dtype=ac, world_size=world,
-                            fused_prep=args.arm == "ours")
+                            fused_prep=args.arm == "ours", scaler=scaler)
 
     def barrier():
         if dist is not None:
@@ -114,7 +116,7 @@ def mode_train(args):
         ms = float(t[0])
         print(json.dumps({"mode": "train", "arm": args.arm, "n_gpus": world,
                           "config": f"two-stream YOLOv5{args.size} training step, {args.imgsz}x{args.imgsz} synthetic pairs, batch "
-                                    f"{args.batch}/GPU, autocast {args.autocast}, SGD, DDP bucket {args.bucket_mb} MB, "
+                                    f"{args.batch}/GPU, autocast {args.autocast}{' + GradScaler' if scaler is not None else ''}, SGD, DDP bucket {args.bucket_mb} MB, "
                                     f"{'channels_last' if args.channels_last else 'NCHW'} backbone",
                           "pairs_per_s": round(world * args.batch / (ms * 1e-3), 2), "ms_per_step": round(ms, 3),
                           "params": nparam, "allreduce_bytes_per_step": nparam * 4 if world > 1 else 0,
@@ -165,7 +167,8 @@ def main():
     ap.add_argument("--arm", default="ours", choices=["ours", "pytorch"])
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--autocast", default="bf16")
+    ap.add_argument("--autocast", default="fp16", choices=["fp16", "bf16", "fp32"],
+                    help="fp16 (+ GradScaler) is the reference's own recipe, train.py:706/:784")
     ap.add_argument("--dtype", default="fp16")
     ap.add_argument("--conf", type=float, default=0.25)
     ap.add_argument("--bucket-mb", dest="bucket_mb", type=int, default=8)

@@ -29,7 +29,8 @@ if a.mode == "train":
     hyp = H.scale_hyp(model, 6, a.imgsz)
     cl = ref.loss.ComputeLoss(model)
     opt = H.make_optimizer(model, hyp, a.batch)
-    step = lambda: H.train_step(model, cl, opt, imgs, targets, autocast_dtype=torch.bfloat16, fused_prep=a.arm == "ours")
+    scaler = H.make_scaler(torch.float16)
+    step = lambda: H.train_step(model, cl, opt, imgs, targets, autocast_dtype=torch.float16, fused_prep=a.arm == "ours", scaler=scaler)
 else:
     model = H.prepare_inference(model, torch.float16, channels_last=a.cl)
     from mmidet_b200 import postprocess

@@ -86,6 +86,25 @@ def test_training_step_both_arms(H):
     assert abs(losses["ours"] - losses["pytorch"]) <= 1e-3 * abs(losses["pytorch"])
 
 
+def test_training_step_fp16_with_grad_scaler(H):
+    """the reference's own precision recipe (train.py:706, :784-801): fp16 autocast + GradScaler.  Three steps on the CUDA
+    fusion path: finite loss every step, the scaler stays positive and the weights move once a step is not skipped."""
+    ref = H.import_reference()
+    model = H.build_detector("s", "ours", seed=0, channels_last=True).train()
+    hyp = H.scale_hyp(model, 6, 320)
+    cl = ref.loss.ComputeLoss(model)
+    opt = H.make_optimizer(model, hyp, 2)
+    scaler = H.make_scaler(torch.float16)
+    assert scaler is not None and H.make_scaler(torch.bfloat16) is None and H.make_scaler(None) is None
+    imgs, targets = H.synthetic_batch(2, 320, seed=6)
+    w0 = [p.detach().clone() for p in model.parameters()][:8]
+    for _ in range(3):
+        loss = H.train_step(model, cl, opt, imgs, targets, autocast_dtype=torch.float16, scaler=scaler)
+        assert bool(torch.isfinite(loss))
+    assert scaler.get_scale() > 0
+    assert any(not torch.equal(a, b.detach()) for a, b in zip(w0, model.parameters()))
+
+
 def test_quiet_removes_the_per_step_prints(H, capsys):
     """the reference prints CUDA tensors (a device sync each) from forward_once and ComputeLoss; quiet()
     shadows `print` in those modules without touching their source, and un-quieting restores it."""
