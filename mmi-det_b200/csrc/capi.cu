@@ -182,36 +182,40 @@ int64_t mmi_pscan_ws_bytes(int B, int L, int D, int N) {
     return pscan_ws_bytes(B, L, D, N);
 }
 
-static int check_pscan(const char *who, int B, int L, int D, int N) {
+static int check_pscan(const char *who, const void *ws, int B, int L, int D, int N) {
     if (B <= 0 || L <= 0 || D <= 0 || N <= 0) { set_error("%s: B, L, D, N must be positive", who); return MMI_ERR_ARG; }
     if (B > 65535) { set_error("%s: B=%d exceeds 65535", who, B); return MMI_ERR_ARG; }
     if (int64_t(D) * N > (int64_t(1) << 30)) { set_error("%s: D*N too large", who); return MMI_ERR_ARG; }
+    // one CTA per (batch, 32-step segment, 128 columns): the grid is one-dimensional
+    const int64_t items = int64_t(B) * ((L + 31) / 32) * ((int64_t(D) * N + 127) / 128);
+    if (items > 0x7fffffffLL) { set_error("%s: B * ceil(L/32) * ceil(D*N/128) = %lld exceeds the grid limit", who, (long long)items); return MMI_ERR_ARG; }
+    if (reinterpret_cast<uintptr_t>(ws) & 15) { set_error("%s: the workspace must be 16-byte aligned (128-bit records)", who); return MMI_ERR_ARG; }
     return require_device();
 }
 
 int mmi_pscan_fwd(const float *A, const float *X, float *H, void *ws, int B, int L, int D, int N, void *stream) {
     if (!A || !X || !H || !ws) { set_error("mmi_pscan_fwd: null pointer"); return MMI_ERR_ARG; }
-    if (int e = check_pscan("mmi_pscan_fwd", B, L, D, N)) return e;
+    if (int e = check_pscan("mmi_pscan_fwd", ws, B, L, D, N)) return e;
     return pscan_fwd_launch(A, X, H, static_cast<float *>(ws), B, L, D * N, static_cast<cudaStream_t>(stream));
 }
 
 int mmi_pscan_bwd(const float *A, const float *H, const float *gH, float *gA, float *gX, void *ws, int B, int L, int D,
                   int N, void *stream) {
     if (!A || !H || !gH || !gA || !gX || !ws) { set_error("mmi_pscan_bwd: null pointer"); return MMI_ERR_ARG; }
-    if (int e = check_pscan("mmi_pscan_bwd", B, L, D, N)) return e;
+    if (int e = check_pscan("mmi_pscan_bwd", ws, B, L, D, N)) return e;
     return pscan_bwd_launch(A, H, gH, gA, gX, static_cast<float *>(ws), B, L, D * N, static_cast<cudaStream_t>(stream));
 }
 
 int mmi_pscan_fwd_f64(const double *A, const double *X, double *H, void *ws, int B, int L, int D, int N, void *stream) {
     if (!A || !X || !H || !ws) { set_error("mmi_pscan_fwd_f64: null pointer"); return MMI_ERR_ARG; }
-    if (int e = check_pscan("mmi_pscan_fwd_f64", B, L, D, N)) return e;
+    if (int e = check_pscan("mmi_pscan_fwd_f64", ws, B, L, D, N)) return e;
     return pscan_fwd_launch_f64(A, X, H, static_cast<double *>(ws), B, L, D * N, static_cast<cudaStream_t>(stream));
 }
 
 int mmi_pscan_bwd_f64(const double *A, const double *H, const double *gH, double *gA, double *gX, void *ws, int B, int L, int D,
                       int N, void *stream) {
     if (!A || !H || !gH || !gA || !gX || !ws) { set_error("mmi_pscan_bwd_f64: null pointer"); return MMI_ERR_ARG; }
-    if (int e = check_pscan("mmi_pscan_bwd_f64", B, L, D, N)) return e;
+    if (int e = check_pscan("mmi_pscan_bwd_f64", ws, B, L, D, N)) return e;
     return pscan_bwd_launch_f64(A, H, gH, gA, gX, static_cast<double *>(ws), B, L, D * N, static_cast<cudaStream_t>(stream));
 }
 
