@@ -47,6 +47,26 @@ def test_pscan_vs_oracle_multi_segment(shape):
     assert relerr(gX.cpu().numpy(), gX64) <= 1e-4
 
 
+def test_pscan_one_long_chain():
+    """a single (batch, column block) chain of 2000 segments: every resident CTA belongs to the same chain, so the look-back
+    regularly runs into its depth limit and has to wait for an inclusive state (the path the wide shapes rarely take)."""
+    from mmidet_b200.pscan import pscan
+    rng = np.random.default_rng(12)
+    shape = (1, 64000, 8, 16)
+    A = (rng.random(shape) * 0.2 + 0.8).astype(np.float32)
+    X = rng.standard_normal(shape).astype(np.float32)
+    gH = rng.standard_normal(shape).astype(np.float32)
+    At, Xt = _t(A).requires_grad_(True), _t(X).requires_grad_(True)
+    H = pscan(At, Xt)
+    gA, gX = torch.autograd.grad(H, (At, Xt), _t(gH))
+    H64 = O.pscan_seq_fwd(A.astype(np.float64), X.astype(np.float64))
+    gA64, gX64 = O.pscan_seq_bwd(A.astype(np.float64), H64, gH.astype(np.float64))
+    assert relerr(H.detach().cpu().numpy(), H64) <= 1e-4
+    assert relerr(gA.cpu().numpy(), gA64) <= 1e-4 and relerr(gX.cpu().numpy(), gX64) <= 1e-4
+    H2 = pscan(At, Xt)
+    assert torch.equal(H.detach(), H2.detach())
+
+
 def test_pscan_is_bit_reproducible():
     """the look-back chains the parked aggregates oldest first, so the value does not depend on how deep each thread had to
     look: repeated runs give identical bits, forward and backward."""
