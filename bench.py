@@ -259,6 +259,7 @@ def detector_train_leg(rank, world, local_rank, dist, steps=8, warmup=5):
     from mmidet_b200 import harness as H
     ref = H.import_reference()
     B, imgsz = 16, 640
+    H.training_backend_flags()  # cudnn.benchmark = True, as the reference's train.py:66 sets it
     model = H.build_detector("l", "ours", seed=0, channels_last=True).train()
     hyp = H.scale_hyp(model, 6, imgsz)
     compute_loss = ref.loss.ComputeLoss(model)

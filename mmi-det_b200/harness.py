@@ -11,6 +11,7 @@ the reference's own drivers do inline:
     synthetic_batch / prep_inputs     train.py:741-745 (uint8 batch -> float / 255 -> RGB | IR split), SURVEY 8d config 4
     make_optimizer / scale_hyp        train.py:567-587, :688-696 (SGD groups by module attribute; bare Parameters such as
                                       A_log / D land in no group, SURVEY App. B -- kept, it is the reference's behaviour)
+    training_backend_flags            train.py:66 (cudnn.benchmark as the reference's init_seeds sets it)
     train_step / make_scaler          train.py:783-804, :706 (fp16 autocast forward, ComputeLoss, scaled backward, optimizer step)
     infer                             detect_twostream.py:88-94 (model forward + non_max_suppression timing window)
     load_checkpoint                   models/experimental.py:113-134 (attempt_load) for the checkpoints train.py:882-894 writes
@@ -219,6 +220,12 @@ def prep_inputs(imgs_u8: torch.Tensor, dtype=torch.float32):
     the fused kernel (csrc/detect.cu) instead of .float(), / 255 and two strided slice copies."""
     from . import postprocess
     return postprocess.split_normalize(imgs_u8, dtype)
+
+
+def training_backend_flags():
+    """train.py:66 -> utils/general.py init_seeds(2 + rank) -> utils/torch_utils.py:42-45: with a non-zero seed the reference
+    trains with `cudnn.benchmark = True, cudnn.deterministic = False` (cuDNN picks each convolution's algorithm by timing)."""
+    torch.backends.cudnn.benchmark, torch.backends.cudnn.deterministic = True, False
 
 
 def make_scaler(autocast_dtype=torch.float16):

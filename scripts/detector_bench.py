@@ -74,6 +74,8 @@ def mode_train(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    if not args.no_cudnn_benchmark:
+        H.training_backend_flags()  # cudnn.benchmark = True, as the reference's train.py sets it
     model = H.build_detector(args.size, args.arm, seed=0, channels_last=args.channels_last).train()
     hyp = H.scale_hyp(model, 6, args.imgsz)
     ref = H.import_reference()
@@ -174,6 +176,7 @@ def main():
     ap.add_argument("--bucket-mb", dest="bucket_mb", type=int, default=8)
     ap.add_argument("--channels-last", dest="channels_last", action="store_true")
     ap.add_argument("--no-fuse", dest="no_fuse", action="store_true")
+    ap.add_argument("--no-cudnn-benchmark", dest="no_cudnn_benchmark", action="store_true")
     args = ap.parse_args()
     d = {"logits": ("s", 640, 1), "train": ("l", 640, 16), "infer": ("x", 1280, 32)}[args.mode]
     args.size = args.size or d[0]
